@@ -1,0 +1,351 @@
+"""Device-resident ADMM loop shared by ADMM_MGL / ADMM_SGL / block_SGL.
+
+torch is used for device memory, streams and host<->device copies only; every arithmetic step
+of the iteration is a hand-written sm_100a kernel reached through the C ABI (_lib.py).
+One iteration (reference: src/gglasso/solver/admm_solver.py:172-246) is
+
+    gg_build_w -> gg_eigh -> gg_recon(phi+) -> gg_prox_* [-> gg_eigh -> gg_recon(shrink) -> gg_dual_update]
+    -> gg_stop_update
+
+and rho, the pending dual rescale, the residual history and the done flag stay on the device,
+so the host only polls the done flag every ``check_every`` iterations.
+"""
+import ctypes
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CTRL_STRIDE, HIST_STRIDE, NPART, C_DONE, C_ITER, C_RHO
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.GGLassoB200Error("gglasso_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_dev(a, dev):
+    """numpy (or torch) -> contiguous FP64 device tensor (copy)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=torch.float64, copy=True).contiguous()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return torch.from_numpy(a).to(dev, non_blocking=False)
+
+
+class Eigh:
+    """workspace + call wrapper for gg_eigh / gg_recon on (M,p,p) stacks."""
+
+    def __init__(self, M, p, dev):
+        self.lib = _lib.load()
+        self.M, self.p = M, p
+        self.ws_bytes = int(self.lib.gg_eigh_workspace_bytes(M, p))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.D = torch.empty((M, p), dtype=torch.float64, device=dev)
+        self.info = (ctypes.c_int * 4)()
+        self.nb2 = _env_int("GG_BLOCK_NB2", 0)
+        self.quad_tol = float(os.environ.get("GG_QUAD_TOL", "1e-10"))
+        self.sweeps = []
+
+    def eigh(self, A, ctrl=None, mpp=1, vectors=1, stream=0):
+        rc = self.lib.gg_eigh(_p(A), _p(self.D), self.M, self.p, _p(ctrl), mpp, _p(self.ws), self.ws_bytes,
+                              vectors, self.nb2, 0.0, 0, self.quad_tol, self.info, stream)
+        _lib.check(rc, "gg_eigh")
+        self.sweeps.append(self.info[0])
+        return self.D
+
+    def recon(self, Vt, out, mode, bnum=None, ctrl=None, mpp=1, stream=0):
+        rc = self.lib.gg_recon(_p(Vt), _p(self.D), _p(bnum), _p(ctrl), mpp, mode, self.M, self.p, _p(out), stream)
+        _lib.check(rc, "gg_recon")
+        return out
+
+
+def eigh(A):
+    """Public helper: batched symmetric eigendecomposition of (M,p,p) / (p,p) numpy input on the GPU.
+
+    Returns (D ascending, Q with eigenvectors as columns) like np.linalg.eigh.
+    """
+    dev = require_cuda()
+    A = np.asarray(A, dtype=np.float64)
+    single = A.ndim == 2
+    At = to_dev(A[None] if single else A, dev)
+    M, p, _ = At.shape
+    e = Eigh(M, p, dev)
+    D = e.eigh(At, stream=torch.cuda.current_stream().cuda_stream)
+    D, order = torch.sort(D, dim=1)
+    Vt = torch.gather(At, 1, order[:, :, None].expand(M, p, p))
+    Q = Vt.transpose(1, 2).contiguous()
+    D, Q = D.cpu().numpy(), Q.cpu().numpy()
+    return (D[0], Q[0]) if single else (D, Q)
+
+
+class AdmmState:
+    """Device buffers of one batched ADMM run: M matrices, ``mpp`` per problem."""
+
+    def __init__(self, S, Omega_0, Theta_0, X_0, mpp, rho, max_iter, latent, nk=None, mu=None, lam_mat=None):
+        self.lib = _lib.load()
+        self.dev = dev = require_cuda()
+        self.S = to_dev(S, dev)
+        self.M, self.p, _ = self.S.shape
+        self.mpp = mpp
+        self.nprob = self.M // mpp
+        self.latent = latent
+        self.Omega = to_dev(Omega_0, dev)
+        self.Omega_new = torch.empty_like(self.Omega)
+        self._bufA, self._bufB = self.Omega, self.Omega_new
+        self.nswap = 0
+        self.Theta = to_dev(Theta_0, dev)
+        self.X = to_dev(X_0, dev)
+        self.L = torch.zeros_like(self.S) if latent else None
+        self.W = torch.empty_like(self.S)
+        self.eig = Eigh(self.M, self.p, dev)
+        self.nk = None if nk is None else to_dev(nk, dev)
+        self.mu = None if mu is None else to_dev(mu, dev)
+        self.lam_mat = None if lam_mat is None else to_dev(lam_mat, dev)
+        ctrl = np.zeros((self.nprob, CTRL_STRIDE))
+        ctrl[:, C_RHO] = rho
+        ctrl[:, 1] = 1.0
+        self.ctrl = to_dev(ctrl, dev)
+        self.hist_cap = max_iter
+        self.hist = torch.zeros((self.nprob, max_iter, HIST_STRIDE), dtype=torch.float64, device=dev)
+        p = self.p
+        self.pdim = to_dev(np.full(self.nprob, mpp * ((p ** 2 + p) / 2)), dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    # -- one Omega step: W build, eigh, phi+ reconstruction into Omega_new -----------------
+    def omega_step(self):
+        lib, st = self.lib, self.stream
+        _lib.check(lib.gg_build_w(_p(self.Theta), _p(self.L), _p(self.X), _p(self.S), _p(self.nk), _p(self.ctrl),
+                                  self.M, self.p, self.mpp, _p(self.W), st), "gg_build_w")
+        self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+        self.eig.recon(self.W, self.Omega_new, 0, bnum=self.nk, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+
+    def l_step(self):
+        """latent: W holds C = Theta - X - Omega; L = V max(D - mu/rho, 0) V^T."""
+        st = self.stream
+        self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+        self.eig.recon(self.W, self.L, 1, bnum=self.mu, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+
+    def swap(self):
+        self.Omega, self.Omega_new = self.Omega_new, self.Omega
+        self.nswap += 1
+
+    def final_omega(self, iters):
+        """Omega of problem q lives in the buffer written by its last *executed* iteration (kernels are
+        no-ops once a problem is done, while the host keeps alternating the two buffers)."""
+        bufs = (self._bufA, self._bufB)            # iteration t (1-based) writes bufs[t % 2]
+        it = torch.as_tensor(np.asarray(iters), device=self.dev).repeat_interleave(self.mpp)
+        odd = (it % 2 == 1).reshape(-1, 1, 1)
+        return torch.where(odd, bufs[1], bufs[0])
+
+    def read_ctrl(self):
+        return self.ctrl.cpu().numpy()
+
+    def finish_x(self):
+        _lib.check(self.lib.gg_scale_pending(_p(self.X), _p(self.ctrl), self.M, self.p, self.mpp, self.stream),
+                   "gg_scale_pending")
+
+    def asym_max(self, A):
+        n = self.lib.gg_sgl_nparts(self.p, self.M)
+        out = torch.empty((self.M, n), dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.gg_asym_max(_p(A), self.M, self.p, _p(out), self.stream), "gg_asym_max")
+        return float(out.max().item())
+
+    def min_eig(self, A):
+        """smallest eigenvalue over the stack (post-loop PD checks; reference uses eigvalsh)."""
+        B = A.clone()
+        D = self.eig.eigh(B, ctrl=None, mpp=1, vectors=0, stream=self.stream)
+        return float(D.min().item())
+
+
+def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None, lam_mat=None, rho=1.0,
+             max_iter=1000, tol=1e-7, rtol=1e-4, stopping_criterion="boyd", update_rho=True, verbose=False,
+             measure=False, latent=False, mu=None, nk=None, header=None, check_every=None, trace=None):
+    """Run the device ADMM loop.  ``kind``: 'mgl' (one problem of K matrices) or 'sgl' (M problems).
+
+    Returns (state, info) where info carries iteration counts, status and histories (numpy).
+    """
+    S3 = S if S.ndim == 3 else S[None]
+    M, p, _ = S3.shape
+    mpp = M if kind == "mgl" else 1
+    st = AdmmState(S3, Omega_0.reshape(S3.shape), Theta_0.reshape(S3.shape), X_0.reshape(S3.shape), mpp, rho,
+                   max_iter, latent, nk=nk, mu=mu, lam_mat=lam_mat)
+    lib, stream = st.lib, st.stream
+    nprob = st.nprob
+    regi = {"GGL": 0, "FGL": 1}.get(reg, -1)
+
+    if kind == "mgl":
+        nt = lib.gg_mgl_ntile(p)
+        nparts_fused = nt * nt
+    else:
+        nparts_fused = lib.gg_sgl_nparts(p, M)
+    nparts_dual = lib.gg_sgl_nparts(p, M) * mpp
+    nparts = nparts_dual if latent else nparts_fused
+    partials = torch.zeros((nprob, max(nparts_fused, nparts_dual), NPART), dtype=torch.float64, device=st.dev)
+
+    if check_every is None:
+        check_every = 1 if (measure or verbose or p > 400) else 4
+    runtime = np.zeros(max_iter)
+    objective = np.zeros(max_iter)
+    kkt_res = np.zeros(max_iter)
+    obj_parts = None
+    it_done = 0
+    status = ""
+
+    if verbose and header:
+        print(header)
+        if stopping_criterion == "boyd":
+            print("%4s\t%10s\t%10s\t%10s\t%10s" % ("iter", "r_t", "s_t", "eps_pri", "eps_dual"))
+        else:
+            print("%4s\t%10s" % ("iter", "kkt residual"))
+    printed = 0
+
+    for it in range(max_iter):
+        if measure:
+            torch.cuda.synchronize()
+            t0 = time.time()
+        st.omega_step()
+        C = st.W if latent else None
+        if kind == "mgl":
+            _lib.check(lib.gg_prox_mgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
+                                       _p(st.ctrl), lambda1, lambda2, regi, M, p, _p(partials), stream),
+                       "gg_prox_mgl")
+        else:
+            _lib.check(lib.gg_prox_sgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
+                                       _p(st.ctrl), float(lambda1), _p(st.lam_mat), M, p, _p(partials), stream),
+                       "gg_prox_sgl")
+        if latent:
+            st.l_step()
+            _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L),
+                                          _p(st.ctrl), M, p, mpp, 1 if kind == "sgl" else 0, _p(partials), stream),
+                       "gg_dual_update")
+        if measure:
+            torch.cuda.synchronize()
+            runtime[it] = time.time() - t0
+            if kind == "mgl":
+                objective[it] = _objective(st, st.Omega_new, lambda1, lambda2, regi)
+        it_done = it + 1
+        if stopping_criterion == "boyd":
+            _lib.check(lib.gg_stop_update(_p(partials), nparts, _p(st.ctrl), _p(st.hist), st.hist_cap, _p(st.pdim),
+                                          tol, rtol, 1 if update_rho else 0, nprob, stream), "gg_stop_update")
+            st.swap()
+            if trace is not None:       # test hook: per-iteration state (X before the rho rescale, like the oracle)
+                if st.ctrl[0, C_DONE].item() == 0 or st.ctrl[0, C_ITER].item() == it + 1:
+                    trace.append(dict(Omega=st.Omega.cpu().numpy(), Theta=st.Theta.cpu().numpy(),
+                                      L=None if st.L is None else st.L.cpu().numpy(), X=st.X.cpu().numpy()))
+            if (it + 1) % check_every == 0 or it + 1 == max_iter:
+                ctrl = st.read_ctrl()
+                if verbose and nprob == 1:
+                    h = st.hist[0, printed:int(ctrl[0, C_ITER])].cpu().numpy()
+                    for row in h:
+                        print("%4d\t%10.4g\t%10.4g\t%10.4g\t%10.4g" % (printed, row[0], row[1], row[2], row[3]))
+                        printed += 1
+                if np.all(ctrl[:, C_DONE] != 0):
+                    break
+        else:
+            st.swap()
+            eta = _kkt_residual(kind, st, lambda1, lambda2, regi, latent)
+            kkt_res[it] = eta
+            if verbose:
+                print("%4d\t%10.4g" % (it, eta))
+            if eta <= tol:
+                status = "optimal"
+                break
+
+    st.finish_x()
+    ctrl = st.read_ctrl()
+    info = {"ctrl": ctrl}
+    if stopping_criterion == "boyd":
+        iters = ctrl[:, C_ITER].astype(int)
+        hist = st.hist.cpu().numpy()
+        info["iters"] = iters
+        info["hist"] = hist
+        statuses = []
+        for q in range(nprob):
+            n = iters[q]
+            r, s, e_pri, e_dual = hist[q, n - 1, :4]
+            if ctrl[q, C_DONE] != 0:
+                statuses.append("optimal")
+            elif r <= e_pri:
+                statuses.append("primal optimal")
+            elif s <= e_dual:
+                statuses.append("dual optimal")
+            else:
+                statuses.append("max iterations reached")
+        info["status"] = statuses
+        info["residual"] = [np.maximum(hist[q, :iters[q], 0], hist[q, :iters[q], 1]) for q in range(nprob)]
+    else:
+        info["iters"] = np.full(nprob, it_done)
+        info["status"] = [status if status else "max iterations reached"] * nprob
+        info["residual"] = [kkt_res[:it_done]] * nprob
+    info["runtime"] = runtime
+    info["objective"] = objective
+    return st, info
+
+
+def _objective(st, Omega, lambda1, lambda2, regi):
+    """f(Omega,S) + P(Theta) (admm_solver.py:213); -log det from the eigenvalues already on the device."""
+    lib = st.lib
+    n = lib.gg_objective_nparts(st.p)
+    parts = torch.empty((n, 2), dtype=torch.float64, device=st.dev)
+    _lib.check(lib.gg_objective(_p(Omega), _p(st.S), _p(st.Theta), lambda1, lambda2, regi, st.M, st.p, _p(parts),
+                                st.stream), "gg_objective")
+    B = Omega.clone()
+    D = st.eig.eigh(B, ctrl=None, mpp=1, vectors=0, stream=st.stream)
+    logdet = torch.log(D).sum()
+    tot = parts.sum(0)
+    return float((-logdet + tot[0] + tot[1]).item())
+
+
+def _kkt_residual(kind, st, lambda1, lambda2, regi, latent):
+    """KKT residual (admm_solver.py:333-371, single_admm_solver.py:293-319) from the device kernels.
+
+    Elementwise glue (differences / norms of already-computed arrays) uses torch on the device;
+    prox, eigendecomposition and spectral maps go through the same CUDA kernels as the loop.
+    """
+    lib, stream = st.lib, st.stream
+    M, p = st.M, st.p
+    ctrl1 = torch.zeros((st.nprob, CTRL_STRIDE), dtype=torch.float64, device=st.dev)
+    ctrl1[:, C_RHO] = 1.0
+    ctrl1[:, 1] = 1.0
+    rho = st.ctrl[:, C_RHO].reshape(-1, 1, 1).repeat_interleave(st.mpp, 0)
+    Xu = rho * st.X                                     # unscaled dual
+    Omega, Theta = st.Omega, st.Theta
+    L = st.L if latent else torch.zeros_like(Theta)
+    zero = torch.zeros_like(Theta)
+    P = torch.empty_like(Theta)
+    Cdummy = torch.empty_like(Theta)
+    if kind == "mgl":
+        _lib.check(lib.gg_prox_mgl(_p(Theta), _p(Theta), _p(Xu), _p(zero), _p(P), _p(Cdummy), _p(ctrl1), lambda1,
+                                   lambda2, regi, M, p, None, stream), "gg_prox_mgl")
+    else:
+        _lib.check(lib.gg_prox_sgl(_p(Theta), _p(Theta), _p(Xu), _p(zero), _p(P), _p(Cdummy), _p(ctrl1),
+                                   float(lambda1), _p(st.lam_mat), M, p, None, stream), "gg_prox_sgl")
+    nT = torch.linalg.norm(Theta)
+    t1 = torch.linalg.norm(Theta - P) / (1 + nT)
+    t2 = torch.linalg.norm(Theta - Omega - L) / (1 + nT)
+    nk = st.nk.reshape(-1, 1, 1) if st.nk is not None else 1.0
+    A = (Omega - nk * st.S - Xu).contiguous()
+    st.eig.eigh(A, stream=stream)
+    st.eig.recon(A, P, 0, bnum=st.nk, ctrl=None, stream=stream)
+    t3 = torch.linalg.norm(Omega - P) / (1 + torch.linalg.norm(Omega))
+    t4 = torch.zeros((), dtype=torch.float64, device=st.dev)
+    if latent:
+        A = (L - Xu).contiguous()
+        st.eig.eigh(A, stream=stream)
+        st.eig.recon(A, P, 1, bnum=st.mu, ctrl=None, stream=stream)
+        t4 = torch.linalg.norm(L - P) / (1 + torch.linalg.norm(L))
+    return float(torch.stack([t1, t2, t3, t4]).max().item())

@@ -1,0 +1,108 @@
+// gg_capi.cu -- extern "C" ABI (include/gglasso_b200.h) over the kernel launchers.
+#include "../../include/gglasso_b200.h"
+#include <cuda_runtime.h>
+#include "gg_condat.cuh"
+
+int gg_launch_build_w(const double*, const double*, double*, const double*, const double*, const double*, int, int,
+                      int, double*, cudaStream_t);
+int gg_launch_prox_sgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
+                       const double*, int, int, double*, cudaStream_t);
+int gg_launch_dual_update(double*, const double*, const double*, const double*, const double*, const double*, int,
+                          int, int, int, double*, cudaStream_t);
+int gg_launch_prox_mgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
+                       double, int, int, int, double*, cudaStream_t);
+int gg_launch_stop_update(const double*, int, double*, double*, int, const double*, double, double, int, int,
+                          cudaStream_t);
+int gg_launch_scale_pending(double*, double*, int, int, int, cudaStream_t);
+int gg_launch_objective(const double*, const double*, const double*, double, double, int, int, int, double*,
+                        cudaStream_t);
+int gg_launch_asym_max(const double*, int, int, double*, cudaStream_t);
+int gg_launch_recon(const double*, const double*, const double*, const double*, int, int, int, int, double*,
+                    cudaStream_t);
+size_t gg_eigh_ws_bytes(int, int);
+int gg_eigh_impl(double*, double*, int, int, const double*, int, void*, size_t, int, int, double, int, double, int*,
+                 cudaStream_t);
+
+extern "C" {
+
+int gg_version(void) { return 100; }
+
+int gg_build_w(const double* Theta, const double* L, double* X, const double* S, const double* nk,
+               const double* ctrl, int M, int p, int mpp, double* W, void* stream)
+{
+    if (M <= 0 || p <= 0 || mpp <= 0) return -1;
+    return gg_launch_build_w(Theta, L, X, S, nk, ctrl, M, p, mpp, W, (cudaStream_t)stream);
+}
+
+size_t gg_eigh_workspace_bytes(int M, int p) { return gg_eigh_ws_bytes(M, p); }
+
+int gg_eigh(double* A, double* D, int M, int p, const double* ctrl, int mpp, void* ws, size_t ws_bytes,
+            int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, void* stream)
+{
+    if (M < 0 || p < 0 || mpp <= 0) return -1;
+    return gg_eigh_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, vectors, block_nb2, tol, max_sweeps, quad_tol, info,
+                        (cudaStream_t)stream);
+}
+
+int gg_recon(const double* Vt, const double* D, const double* bnum, const double* ctrl, int mpp, int mode, int M,
+             int p, double* Out, void* stream)
+{
+    if (M <= 0 || p <= 0 || mpp <= 0 || mode < 0 || mode > 2) return -1;
+    return gg_launch_recon(Vt, D, bnum, ctrl, mpp, mode, M, p, Out, (cudaStream_t)stream);
+}
+
+int gg_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta, double* C,
+                const double* ctrl, double lam, const double* lam_mat, int M, int p, double* partials, void* stream)
+{
+    if (M <= 0 || p <= 0) return -1;
+    return gg_launch_prox_sgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, M, p, partials,
+                              (cudaStream_t)stream);
+}
+
+int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta, double* C,
+                const double* ctrl, double lambda1, double lambda2, int reg, int K, int p, double* partials,
+                void* stream)
+{
+    if (K <= 0 || p <= 0 || reg < 0 || reg > 1) return -1;
+    return gg_launch_prox_mgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lambda1, lambda2, reg, K, p, partials,
+                              (cudaStream_t)stream);
+}
+
+int gg_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta, const double* L,
+                   const double* ctrl, int M, int p, int mpp, int sgl_order, double* partials, void* stream)
+{
+    if (M <= 0 || p <= 0 || mpp <= 0) return -1;
+    return gg_launch_dual_update(X, Omega, Omega_prev, Theta, L, ctrl, M, p, mpp, sgl_order, partials,
+                                 (cudaStream_t)stream);
+}
+
+int gg_stop_update(const double* partials, int nparts, double* ctrl, double* hist, int hist_cap, const double* pdim,
+                   double tol, double rtol, int update_rho, int nprob, void* stream)
+{
+    if (nparts <= 0 || nprob <= 0) return -1;
+    return gg_launch_stop_update(partials, nparts, ctrl, hist, hist_cap, pdim, tol, rtol, update_rho, nprob,
+                                 (cudaStream_t)stream);
+}
+
+int gg_scale_pending(double* X, double* ctrl, int M, int p, int mpp, void* stream)
+{
+    if (M <= 0 || p <= 0 || mpp <= 0) return -1;
+    return gg_launch_scale_pending(X, ctrl, M, p, mpp, (cudaStream_t)stream);
+}
+
+int gg_objective(const double* Omega, const double* S, const double* Theta, double lambda1, double lambda2, int reg,
+                 int K, int p, double* partials, void* stream)
+{
+    if (K <= 0 || p <= 0) return -1;
+    return gg_launch_objective(Omega, S, Theta, lambda1, lambda2, reg, K, p, partials, (cudaStream_t)stream);
+}
+
+int gg_asym_max(const double* A, int M, int p, double* out, void* stream)
+{
+    if (M <= 0 || p <= 0) return -1;
+    return gg_launch_asym_max(A, M, p, out, (cudaStream_t)stream);
+}
+
+void gg_host_tv1d(double* v, int n, int stride, double lam) { gg_tv1d_inplace(v, n, stride, lam); }
+
+}  // extern "C"

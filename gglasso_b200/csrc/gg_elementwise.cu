@@ -1,0 +1,477 @@
+// gg_elementwise.cu -- HBM-bound kernels of the ADMM iteration (sm_100a).
+//
+//   gg_build_w        W = Theta - L - X - (n_k/rho) S            admm_solver.py:180, single_admm_solver.py:163
+//   gg_prox_sgl       Theta = prox_od_1norm(Omega+L+X, lam/rho)   single_admm_solver.py:169, ggl_helper.py:16-27
+//                     fused with X += Omega - Theta and the five residual partial sums (non-latent)
+//   gg_prox_mgl       Theta = prox_p(Omega+L+X, l1/rho, l2/rho)   admm_solver.py:190-194, ggl_helper.py:190-207
+//                     GGL: ggl_helper.py:68-71,38-43; FGL: ggl_helper.py:131-134 + fgl_helper.py:11-68
+//                     same fusion; one CTA per 16x16 tile pair (I<=J), all K instances, mirrored write
+//   gg_dual_update    X += Omega - Theta + L + partial sums (latent) admm_solver.py:208, single_admm_solver.py:177
+//   gg_stop_update    Boyd residuals, stopping test, rho update    admm_solver.py:216-246,316-331
+//   gg_scale          X *= pending rho_old/rho_new                 admm_solver.py:236
+//
+// Compiled with -fmad=false: these kernels are bandwidth bound and the unfused arithmetic
+// keeps every expression bit-identical to the numpy/numba reference.
+#include "gg_common.cuh"
+#include "gg_condat.cuh"
+
+#define EW_THREADS 256
+#define EW_UNROLL 4
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+build_w_kernel(const double* __restrict__ Theta, const double* __restrict__ L, double* __restrict__ X,
+               const double* __restrict__ S, const double* __restrict__ nk, const double* __restrict__ ctrl,
+               int mpp, size_t pp, double* __restrict__ W)
+{
+    const int m = blockIdx.y;
+    const double* c = ctrl + (size_t)(m / mpp) * GG_CTRL_STRIDE;
+    if (c[GG_C_DONE] != 0.0) return;
+    const double rho = c[GG_C_RHO];
+    const double xs = c[GG_C_XSCALE];
+    const double beta = (nk ? nk[m] : 1.0) / rho;
+    const size_t base = (size_t)m * pp;
+    const size_t stride = (size_t)gridDim.x * EW_THREADS;
+    const bool rescale = (xs != 1.0);
+    for (size_t e0 = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e0 < pp; e0 += stride * EW_UNROLL) {
+        double th[EW_UNROLL], x[EW_UNROLL], s[EW_UNROLL], l[EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            const size_t e = e0 + u * stride;
+            if (e < pp) {
+                th[u] = Theta[base + e];
+                x[u] = X[base + e];
+                s[u] = S[base + e];
+                l[u] = L ? L[base + e] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            const size_t e = e0 + u * stride;
+            if (e < pp) {
+                const double xv = rescale ? xs * x[u] : x[u];
+                double w = th[u];
+                if (L) w = w - l[u];
+                w = w - xv;
+                w = w - beta * s[u];
+                W[base + e] = w;
+                if (rescale) X[base + e] = xv;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SGL prox (+ fused dual update and residual partials when C == nullptr).
+// lam: scalar lambda1, lam_mat: optional (M,p,p) elementwise penalty (lambda1 * mask).
+__global__ void __launch_bounds__(EW_THREADS)
+prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Omega_prev,
+                const double* __restrict__ L, double* __restrict__ X, double* __restrict__ Theta,
+                double* __restrict__ C, const double* __restrict__ ctrl, double lam,
+                const double* __restrict__ lam_mat, int p, double* __restrict__ partials)
+{
+    __shared__ double scratch[GG_NPART * 32];
+    const int m = blockIdx.y;
+    const double* c = ctrl + (size_t)m * GG_CTRL_STRIDE;
+    if (c[GG_C_DONE] != 0.0) return;
+    const double inv_rho = 1.0 / c[GG_C_RHO];
+    const size_t pp = (size_t)p * p;
+    const size_t base = (size_t)m * pp;
+    const size_t stride = (size_t)gridDim.x * EW_THREADS;
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += stride) {
+        const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
+        const double om = Omega[base + e];
+        const double x = X[base + e];
+        const double l = L ? L[base + e] : 0.0;
+        double a = om;
+        if (L) a = a + l;
+        a = a + x;
+        const double thr = inv_rho * (lam_mat ? lam_mat[base + e] : lam);
+        const double th = (i == j) ? a : gg_soft(a, thr);
+        Theta[base + e] = th;
+        if (C) {
+            C[base + e] = (th - x) - om;          // C_t = Theta_t - X_t - Omega_t
+        } else {
+            const double xn = (x + om) - th;      // X_t + Omega_t - Theta_t (+ L_t = 0)
+            X[base + e] = xn;
+            const double d1 = om - th, d2 = om - Omega_prev[base + e];
+            acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+        }
+    }
+    if (!C) {
+        gg_block_sum<GG_NPART>(acc, scratch);
+        if (threadIdx.x == 0) {
+            double* out = partials + ((size_t)m * gridDim.x + blockIdx.x) * GG_NPART;
+#pragma unroll
+            for (int i = 0; i < GG_NPART; ++i) out[i] = acc[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dual update for the latent variants:  X <- X + Omega - Theta + L, plus residual partials.
+__global__ void __launch_bounds__(EW_THREADS)
+dual_update_kernel(double* __restrict__ X, const double* __restrict__ Omega, const double* __restrict__ Omega_prev,
+                   const double* __restrict__ Theta, const double* __restrict__ L, const double* __restrict__ ctrl,
+                   int mpp, size_t pp, int sgl_order, double* __restrict__ partials)
+{
+    __shared__ double scratch[GG_NPART * 32];
+    const int m = blockIdx.y;
+    const double* c = ctrl + (size_t)(m / mpp) * GG_CTRL_STRIDE;
+    if (c[GG_C_DONE] != 0.0) return;
+    const size_t base = (size_t)m * pp;
+    const size_t stride = (size_t)gridDim.x * EW_THREADS;
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += stride) {
+        const double om = Omega[base + e], th = Theta[base + e], l = L[base + e], x = X[base + e];
+        const double res = (om - th) + l;                         // Omega - Theta + L
+        const double xn = sgl_order ? (((x + om) - th) + l) : (x + res);
+        X[base + e] = xn;
+        const double tl = th - l, d2 = om - Omega_prev[base + e];
+        acc[0] += om * om; acc[1] += tl * tl; acc[2] += xn * xn; acc[3] += res * res; acc[4] += d2 * d2;
+    }
+    gg_block_sum<GG_NPART>(acc, scratch);
+    if (threadIdx.x == 0) {
+        double* out = partials + ((size_t)m * gridDim.x + blockIdx.x) * GG_NPART;
+#pragma unroll
+        for (int i = 0; i < GG_NPART; ++i) out[i] = acc[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// MGL prox: one CTA per 16x16 tile pair (I <= J); thread (tr,tc) owns entry (I*16+tr, J*16+tc)
+// and runs the K-vector prox in shared memory (layout [k][tr*17+tc]: conflict-free for any
+// per-thread k, which matters for the data-dependent TV scan).  The mirrored tile (J,I) is
+// produced by reading the same shared values transposed, so global traffic is coalesced both
+// ways and Theta is exactly symmetric, as in the reference (prox_p mirrors the upper triangle).
+#define PT 16
+#define PLD 17
+#define PSLOT (PT * PLD)   // 272
+
+template <int REG, bool LATENT>
+__global__ void __launch_bounds__(PT * PT)
+prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Omega_prev,
+                const double* __restrict__ L, double* __restrict__ X, double* __restrict__ Theta,
+                double* __restrict__ C, const double* __restrict__ ctrl, double lambda1, double lambda2,
+                int K, int p, double* __restrict__ partials)
+{
+    extern __shared__ double ysm[];                 // K * PSLOT
+    __shared__ double scratch[GG_NPART * 32];
+    const int I = blockIdx.y, J = blockIdx.x;
+    if (I > J) return;
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const double inv_rho = 1.0 / ctrl[GG_C_RHO];
+    const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
+    const int tr = threadIdx.x / PT, tc = threadIdx.x % PT;
+    const size_t pp = (size_t)p * p;
+    const int i = I * PT + tr, j = J * PT + tc;
+    const bool valid = (i < p) && (j < p);
+    const bool upper = valid && (I < J || tr <= tc);
+    const int slot = tr * PLD + tc;
+
+    // ---- phase A: gather the K-vector of (Omega + L) + X, prox in place --------------------
+    if (upper) {
+        const size_t e = (size_t)i * p + j;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            double v = Omega[k * pp + e];
+            if (LATENT) v = v + L[k * pp + e];
+            v = v + X[k * pp + e];
+            ysm[k * PSLOT + slot] = v;
+        }
+        if (i != j) {
+            double* y = ysm + slot;
+            if (REG == 0) {            // GGL: group soft threshold of the l1-soft-thresholded vector
+                double ss = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    const double u = gg_soft(y[k * PSLOT], l1);
+                    y[k * PSLOT] = u;
+                    ss += u * u;
+                }
+                const double nrm = sqrt(ss);
+                const double a = nrm > l2 ? nrm : l2;
+                const double f = a - l2;
+                for (int k = 0; k < K; ++k) y[k * PSLOT] = (y[k * PSLOT] * f) / a;
+            } else {                   // FGL: TV prox across k, then l1 soft threshold
+                gg_tv1d_inplace(y, K, PSLOT, l2);
+                for (int k = 0; k < K; ++k) y[k * PSLOT] = gg_soft(y[k * PSLOT], l1);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: write Theta (+C or X and partial sums) for tile (I,J) and its mirror ------
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        int ii, jj, sl;
+        if (side == 0) {
+            ii = i; jj = j;
+            sl = (I < J || tr <= tc) ? slot : (tc * PLD + tr);
+        } else {
+            if (I == J) break;
+            ii = J * PT + tr; jj = I * PT + tc;     // element of tile (J,I)
+            sl = tc * PLD + tr;                     // = value of its transpose (jj, ii)
+        }
+        if (ii < p && jj < p) {
+            const size_t e = (size_t)ii * p + jj;
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const double th = ysm[k * PSLOT + sl];
+                const double om = Omega[k * pp + e];
+                const double x = X[k * pp + e];
+                Theta[k * pp + e] = th;
+                if (LATENT) {
+                    C[k * pp + e] = (th - x) - om;
+                } else {
+                    const double d1 = om - th;
+                    const double xn = x + d1;                  // X += Omega - Theta (+ L = 0)
+                    X[k * pp + e] = xn;
+                    const double d2 = om - Omega_prev[k * pp + e];
+                    acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+                }
+            }
+        }
+    }
+    if (!LATENT) {
+        gg_block_sum<GG_NPART>(acc, scratch);
+        if (threadIdx.x == 0) {
+            double* out = partials + ((size_t)I * gridDim.x + J) * GG_NPART;
+#pragma unroll
+            for (int q = 0; q < GG_NPART; ++q) out[q] = acc[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stopping test + rho update, one CTA per problem; deterministic (fixed-order) reduction.
+__global__ void __launch_bounds__(256)
+stop_update_kernel(const double* __restrict__ partials, int nparts, double* __restrict__ ctrl,
+                   double* __restrict__ hist, int hist_cap, const double* __restrict__ pdim,
+                   double tol, double rtol, int update_rho)
+{
+    __shared__ double scratch[GG_NPART * 32];
+    const int q = blockIdx.x;
+    double* c = ctrl + (size_t)q * GG_CTRL_STRIDE;
+    if (c[GG_C_DONE] != 0.0) return;
+    const double* P = partials + (size_t)q * nparts * GG_NPART;
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int t = threadIdx.x; t < nparts; t += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < GG_NPART; ++i) acc[i] += P[(size_t)t * GG_NPART + i];
+    }
+    gg_block_sum<GG_NPART>(acc, scratch);
+    if (threadIdx.x == 0) {
+        const double rho = c[GG_C_RHO];
+        const double nO = sqrt(acc[0]), nTL = sqrt(acc[1]), nX = sqrt(acc[2]);
+        const double r = sqrt(acc[3]);
+        const double s = rho * sqrt(acc[4]);
+        const double dim = pdim[q];
+        const double e_pri = dim * tol + rtol * fmax(nO, nTL);
+        const double e_dual = dim * tol + rtol * rho * nX;
+        const int it = (int)c[GG_C_ITER];
+        if (it < hist_cap) {
+            double* h = hist + ((size_t)q * hist_cap + it) * GG_HIST_STRIDE;
+            h[0] = r; h[1] = s; h[2] = e_pri; h[3] = e_dual; h[4] = rho;
+        }
+        double rho_new = rho;
+        if (update_rho) {
+            if (r >= 10.0 * s) rho_new = 2.0 * rho;
+            else if (s >= 10.0 * r) rho_new = 0.5 * rho;
+        }
+        c[GG_C_XSCALE] = rho / rho_new;
+        c[GG_C_RHO] = rho_new;
+        c[GG_C_R] = r; c[GG_C_S] = s; c[GG_C_EPRI] = e_pri; c[GG_C_EDUAL] = e_dual;
+        c[GG_C_ITER] = (double)(it + 1);
+        if (r <= e_pri && s <= e_dual) { c[GG_C_STATUS] = 1.0; c[GG_C_DONE] = 1.0; }
+    }
+}
+
+// X *= pending scale (applied once after the loop; inside the loop build_w folds it in).
+__global__ void __launch_bounds__(EW_THREADS)
+scale_pending_kernel(double* __restrict__ X, double* __restrict__ ctrl, int mpp, size_t pp)
+{
+    const int m = blockIdx.y;
+    const double xs = ctrl[(size_t)(m / mpp) * GG_CTRL_STRIDE + GG_C_XSCALE];
+    if (xs == 1.0) return;
+    const size_t base = (size_t)m * pp;
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS)
+        X[base + e] = xs * X[base + e];
+}
+
+__global__ void reset_xscale_kernel(double* ctrl, int nprob)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nprob) ctrl[(size_t)q * GG_CTRL_STRIDE + GG_C_XSCALE] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Objective pieces (measure=True): <Omega,S>, and the regulariser P(Theta) on the strict upper
+// triangle (ggl_helper.py:162-176).  out[0] += <Omega,S>, out[1] += 2*sum(l1*|.|_1 + l2*(|.|_2 or TV)).
+__global__ void __launch_bounds__(EW_THREADS)
+objective_kernel(const double* __restrict__ Omega, const double* __restrict__ S, const double* __restrict__ Theta,
+                 double lambda1, double lambda2, int reg, int K, int p, double* __restrict__ partials)
+{
+    __shared__ double scratch[2 * 32];
+    const size_t pp = (size_t)p * p;
+    double acc[2] = {0.0, 0.0};
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
+        double n1 = 0.0, n2 = 0.0, prev = 0.0;
+        for (int k = 0; k < K; ++k) {
+            acc[0] += Omega[k * pp + e] * S[k * pp + e];
+            if (j > i && reg >= 0) {
+                const double a = Theta[k * pp + e];
+                n1 += fabs(a);
+                if (reg == 0) n2 += a * a;
+                else if (k > 0) n2 += fabs(a - prev);
+                prev = a;
+            }
+        }
+        if (j > i && reg >= 0) {
+            if (reg == 0) n2 = sqrt(n2);
+            acc[1] += lambda1 * n1 + lambda2 * n2;
+        }
+    }
+    gg_block_sum<2>(acc, scratch);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = acc[0];
+        partials[2 * blockIdx.x + 1] = 2.0 * acc[1];
+    }
+}
+
+// max |A - A^T| per stack (symmetry check after the loop: admm_solver.py:284-291)
+__global__ void __launch_bounds__(EW_THREADS)
+asym_max_kernel(const double* __restrict__ A, int p, double* __restrict__ out)
+{
+    __shared__ double scratch[32];
+    const int m = blockIdx.y;
+    const size_t pp = (size_t)p * p;
+    const double* a = A + (size_t)m * pp;
+    double mx = 0.0;
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
+        if (j > i) mx = fmax(mx, fabs(a[e] - a[(size_t)j * p + i]));
+    }
+    mx = gg_block_max(mx, scratch);
+    if (threadIdx.x == 0) out[(size_t)m * gridDim.x + blockIdx.x] = mx;
+}
+
+// ==========================================================================================
+// host launchers (C++ linkage; the extern "C" ABI lives in gg_capi.cu)
+// ==========================================================================================
+static inline int ew_blocks(size_t pp, int M)
+{
+    // enough CTAs to fill 148 SMs x 8 resident CTAs, but no more than the work needs
+    size_t need = (pp + (size_t)EW_THREADS * EW_UNROLL - 1) / ((size_t)EW_THREADS * EW_UNROLL);
+    size_t cap = (size_t)(148 * 8 + M - 1) / M;
+    if (cap < 1) cap = 1;
+    size_t b = need < cap ? need : cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+int gg_launch_build_w(const double* Theta, const double* L, double* X, const double* S, const double* nk,
+                      const double* ctrl, int M, int p, int mpp, double* W, cudaStream_t st)
+{
+    const size_t pp = (size_t)p * p;
+    dim3 grid(ew_blocks(pp, M), M);
+    build_w_kernel<<<grid, EW_THREADS, 0, st>>>(Theta, L, X, S, nk, ctrl, mpp, pp, W);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int gg_sgl_nparts(int p, int M) { return ew_blocks((size_t)p * p, M); }
+
+int gg_launch_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
+                       double* C, const double* ctrl, double lam, const double* lam_mat, int M, int p,
+                       double* partials, cudaStream_t st)
+{
+    dim3 grid(gg_sgl_nparts(p, M), M);
+    prox_sgl_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, p, partials);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta,
+                          const double* L, const double* ctrl, int M, int p, int mpp, int sgl_order,
+                          double* partials, cudaStream_t st)
+{
+    const size_t pp = (size_t)p * p;
+    dim3 grid(gg_sgl_nparts(p, M), M);
+    dual_update_kernel<<<grid, EW_THREADS, 0, st>>>(X, Omega, Omega_prev, Theta, L, ctrl, mpp, pp, sgl_order, partials);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int gg_mgl_ntile(int p) { return (p + PT - 1) / PT; }
+
+template <int REG, bool LATENT>
+static int launch_prox_mgl_t(const double* Omega, const double* Omega_prev, const double* L, double* X,
+                             double* Theta, double* C, const double* ctrl, double l1, double l2, int K, int p,
+                             double* partials, cudaStream_t st)
+{
+    const int nt = gg_mgl_ntile(p);
+    const size_t smem = (size_t)K * PSLOT * sizeof(double);
+    if (smem > 200 * 1024) return -2;   // K too large for the shared-memory layout
+    auto kern = prox_mgl_kernel<REG, LATENT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid(nt, nt);
+    kern<<<grid, PT * PT, smem, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
+                       double* C, const double* ctrl, double l1, double l2, int reg, int K, int p,
+                       double* partials, cudaStream_t st)
+{
+    const bool latent = (C != nullptr);
+    if (reg == 0) {
+        return latent ? launch_prox_mgl_t<0, true>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st)
+                      : launch_prox_mgl_t<0, false>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st);
+    }
+    return latent ? launch_prox_mgl_t<1, true>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st)
+                  : launch_prox_mgl_t<1, false>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st);
+}
+
+int gg_launch_stop_update(const double* partials, int nparts, double* ctrl, double* hist, int hist_cap,
+                          const double* pdim, double tol, double rtol, int update_rho, int nprob, cudaStream_t st)
+{
+    stop_update_kernel<<<nprob, 256, 0, st>>>(partials, nparts, ctrl, hist, hist_cap, pdim, tol, rtol, update_rho);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_scale_pending(double* X, double* ctrl, int M, int p, int mpp, cudaStream_t st)
+{
+    const size_t pp = (size_t)p * p;
+    dim3 grid(ew_blocks(pp, M), M);
+    scale_pending_kernel<<<grid, EW_THREADS, 0, st>>>(X, ctrl, mpp, pp);
+    GG_CHECK_LAUNCH();
+    const int nprob = M / mpp;
+    reset_xscale_kernel<<<(nprob + 127) / 128, 128, 0, st>>>(ctrl, nprob);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int gg_objective_nparts(int p) { return ew_blocks((size_t)p * p, 1); }
+
+int gg_launch_objective(const double* Omega, const double* S, const double* Theta, double l1, double l2, int reg,
+                        int K, int p, double* partials, cudaStream_t st)
+{
+    objective_kernel<<<gg_objective_nparts(p), EW_THREADS, 0, st>>>(Omega, S, Theta, l1, l2, reg, K, p, partials);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_asym_max(const double* A, int M, int p, double* out, cudaStream_t st)
+{
+    dim3 grid(gg_sgl_nparts(p, M), M);
+    asym_max_kernel<<<grid, EW_THREADS, 0, st>>>(A, p, out);
+    GG_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,110 @@
+/*
+ * gglasso_b200.h -- C ABI of the B200 (sm_100a) implementation of GGLasso's ADMM hot path.
+ *
+ * The reference (fabian-sp/GGLasso v0.2.1) is pure Python and has no FFI; its boundary for this
+ * path is three Python callables (ADMM_MGL, ADMM_SGL, block_SGL).  The host side of this repo
+ * (gglasso_b200/solver/) re-implements those callables and drives the entry points below through
+ * ctypes.  Each entry point cites the reference code it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - all matrices are FP64, C-contiguous stacks (M, p, p) in DEVICE memory; M = number of
+ *     matrices in the launch (K instances of one MGL problem, or M independent SGL problems);
+ *   - `mpp` = matrices per ADMM problem (K for MGL, 1 for SGL batches); problem q = m / mpp;
+ *   - `ctrl` = device control block, GG_CTRL_STRIDE doubles per problem (layout below); rho, the
+ *     pending dual rescale and the done flag live there so the loop never needs the host;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative argument error;
+ *   - no entry point allocates device memory: scratch comes from the caller
+ *     (gg_eigh_workspace_bytes).
+ */
+#ifndef GGLASSO_B200_H
+#define GGLASSO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_CTRL_STRIDE 16 /* doubles per problem */
+/* ctrl[0]=rho  ctrl[1]=pending X scale  ctrl[2]=done  ctrl[3]=iterations done
+ * ctrl[4..7]=r,s,eps_pri,eps_dual of the last iteration  ctrl[8]=1 if 'optimal' */
+#define GG_HIST_STRIDE 5  /* per iteration: r, s, eps_pri, eps_dual, rho */
+#define GG_NPART 5        /* partial sums per CTA feeding gg_stop_update */
+
+int gg_version(void);
+
+/* W = Theta - L - X - (n_k/rho) S ; also folds the pending rescale of X (rho_old/rho_new) into X.
+ * reference: src/gglasso/solver/admm_solver.py:180,236 ; single_admm_solver.py:163,205.
+ * L may be NULL (non-latent); nk may be NULL (all ones) or a device array (M). */
+int gg_build_w(const double* Theta, const double* L, double* X, const double* S, const double* nk,
+               const double* ctrl, int M, int p, int mpp, double* W, void* stream);
+
+/* Batched symmetric eigendecomposition (replaces np.linalg.eigh at admm_solver.py:181,199 and
+ * single_admm_solver.py:164,174).  A (M,p,p) is overwritten by Vt: row c of Vt[m] is the unit
+ * eigenvector belonging to D[m][c] (order and signs arbitrary).  vectors=0 skips normalisation
+ * (eigenvalues only).  block_nb2 in {0,32,64,128}: rows per block pair of the large-p path (0 = default).
+ * tol<=0, max_sweeps<=0: defaults.  quad_tol: a sweep whose largest measured off-diagonal cosine is
+ * below quad_tol is taken as the last one (quadratic convergence); 0 disables.  info[0] (host) = sweeps. */
+size_t gg_eigh_workspace_bytes(int M, int p);
+int gg_eigh(double* A, double* D, int M, int p, const double* ctrl, int mpp, void* ws, size_t ws_bytes,
+            int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, void* stream);
+
+/* Out = V diag(f(D)) V^T with V^T = Vt from gg_eigh (FP64 tensor cores, exactly symmetric result).
+ * mode 0: f = phi+(d, beta) = (sqrt(d^2+4 beta)+d)/2   src/gglasso/solver/ggl_helper.py:272-303
+ * mode 1: f = max(d-beta, 0)                            src/gglasso/solver/ggl_helper.py:29-36
+ * mode 2: f = d
+ * beta = bnum[m]/rho (bnum NULL -> 1; ctrl NULL -> rho = 1). */
+int gg_recon(const double* Vt, const double* D, const double* bnum, const double* ctrl, int mpp, int mode,
+             int M, int p, double* Out, void* stream);
+
+/* Theta = prox_od_1norm(Omega + L + X, lam/rho)   src/gglasso/solver/ggl_helper.py:16-27,
+ * single_admm_solver.py:169.  lam_mat (M,p,p) optional elementwise penalty (lambda1*lambda1_mask).
+ * C == NULL (non-latent): fused with X += Omega - Theta (single_admm_solver.py:177) and the partial
+ * sums for gg_stop_update (partials: M * gg_sgl_nparts(p,M) * GG_NPART doubles).
+ * C != NULL (latent): writes C = Theta - X - Omega (single_admm_solver.py:173), X untouched. */
+int gg_sgl_nparts(int p, int M);
+int gg_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
+                double* C, const double* ctrl, double lam, const double* lam_mat, int M, int p,
+                double* partials, void* stream);
+
+/* Theta = prox_p(Omega + L + X, lambda1/rho, lambda2/rho, reg)   src/gglasso/solver/ggl_helper.py:190-207
+ * reg 0 = GGL (ggl_helper.py:68-71,38-43), 1 = FGL (ggl_helper.py:131-134, fgl_helper.py:11-68).
+ * Same fusion/latent convention as gg_prox_sgl; partials: gg_mgl_ntile(p)^2 * GG_NPART doubles,
+ * zero-initialised by the caller once. */
+int gg_mgl_ntile(int p);
+int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
+                double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
+                double* partials, void* stream);
+
+/* X += Omega - Theta + L and partial sums (latent variants)   admm_solver.py:208, single_admm_solver.py:177.
+ * sgl_order selects the association order of the reference's SGL expression. */
+int gg_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta,
+                   const double* L, const double* ctrl, int M, int p, int mpp, int sgl_order,
+                   double* partials, void* stream);
+
+/* Boyd residuals, stopping test and rho update on the device   admm_solver.py:216-246,316-331.
+ * hist: nprob * hist_cap * GG_HIST_STRIDE doubles; pdim[q] = K(p^2+p)/2 of problem q. */
+int gg_stop_update(const double* partials, int nparts, double* ctrl, double* hist, int hist_cap,
+                   const double* pdim, double tol, double rtol, int update_rho, int nprob, void* stream);
+
+/* apply the pending rescale to X after the loop (admm_solver.py:236) and clear it */
+int gg_scale_pending(double* X, double* ctrl, int M, int p, int mpp, void* stream);
+
+/* objective pieces for measure=True   ggl_helper.py:162-176,266-270 ; basic_linalg.py:20-33.
+ * partials: 2 * gg_objective_nparts(p) doubles: {<Omega,S>, P(Theta)} per CTA.  reg -1 skips P. */
+int gg_objective_nparts(int p);
+int gg_objective(const double* Omega, const double* S, const double* Theta, double lambda1, double lambda2,
+                 int reg, int K, int p, double* partials, void* stream);
+
+/* max |A - A^T| partials (symmetry warnings, admm_solver.py:284-291); out: M * gg_sgl_nparts(p,M) doubles */
+int gg_asym_max(const double* A, int M, int p, double* out, void* stream);
+
+/* Host-side execution of the exact device TV-prox routine (unit tests without a GPU). */
+void gg_host_tv1d(double* v, int n, int stride, double lam);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

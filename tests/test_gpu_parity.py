@@ -1,0 +1,358 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+Every test drives the CUDA path through the C ABI (ctypes) or through the reference-signature
+callables and checks it against (a) golden fixtures produced by the real reference and (b) the
+CPU oracle on the same seeded input.  Tolerances follow BASELINE.json's north_star:
+Theta/Omega/L within 1e-8 relative Frobenius per iteration, identical sparsity pattern,
+final objective within 1e-6 relative.
+"""
+import ast
+import contextlib
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+PER_ITER_TOL = 1e-8
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _quiet(fn, *a, **kw):
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        out = fn(*a, **kw)
+    return out, buf.getvalue()
+
+
+def _sym(rng, p, scale=1.0):
+    A = rng.standard_normal((p, p)) * scale
+    return (A + A.T) / 2
+
+
+# --------------------------------------------------------------------------------------------
+# eigensolver + spectral reconstruction
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [1, 2, 3, 10, 37, 100, 160, 161, 200, 333, 512])
+def test_eigh_matches_lapack(p):
+    from gglasso_b200._engine import eigh
+    rng = np.random.default_rng(p)
+    M = 3 if p > 2 else 2
+    A = np.stack([_sym(rng, p) - np.cov(rng.standard_normal((p, 2 * p + 2)), bias=True).reshape(p, p)
+                  for _ in range(M)])
+    A[0] = np.diag(np.arange(p, dtype=float))            # already diagonal
+    if p > 4:
+        A[1][:, :2] = 0.0; A[1][:2, :] = 0.0            # noqa: E702  (exact zero rows -> rank deficient)
+    D, Q = eigh(A)
+    Dref = np.linalg.eigvalsh(A)
+    scale = np.abs(Dref).max(axis=1, keepdims=True) + 1.0
+    assert np.abs(D - Dref).max() < 1e-11 * p ** 0.5 * scale.max()
+    for m in range(M):
+        assert np.abs(Q[m].T @ Q[m] - np.eye(p)).max() < 1e-12
+        assert np.abs(A[m] @ Q[m] - Q[m] * D[m]).max() < 2e-12 * p ** 0.5 * scale[m, 0]
+
+
+def test_eigh_clustered_and_scaled():
+    from gglasso_b200._engine import eigh
+    rng = np.random.default_rng(7)
+    for p in (64, 300):
+        Q, _ = np.linalg.qr(rng.standard_normal((p, p)))
+        d = np.concatenate([np.full(p // 2, 1.0), np.full(p // 4, 1.0 + 1e-9), rng.standard_normal(p - p // 2 - p // 4)])
+        for s in (1e-6, 1.0, 1e5):
+            A = (Q * (s * d)) @ Q.T
+            A = (A + A.T) / 2
+            D, V = eigh(A)
+            assert np.abs(np.sort(D) - np.sort(s * d)).max() < 1e-11 * s * p ** 0.5
+            f = np.exp(-D / s)
+            ref = (Q * np.exp(-d)) @ Q.T
+            assert _rel((V * f) @ V.T, ref) < 1e-10
+
+
+@pytest.mark.parametrize("p", [5, 64, 100, 161, 257, 384])
+def test_recon_modes(p):
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import Eigh, to_dev, _p
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(p + 1)
+    M = 2
+    A = np.stack([_sym(rng, p) for _ in range(M)])
+    D, Q = np.linalg.eigh(A)
+    At = to_dev(A, dev)
+    e = Eigh(M, p, dev)
+    e.eigh(At)
+    out = torch.empty_like(At)
+    bnum = to_dev(np.array([0.7, 1.9]), dev)
+    for mode, f in ((0, lambda d, b: 0.5 * (np.sqrt(d * d + 4 * b) + d)), (1, lambda d, b: np.maximum(d - b, 0)),
+                    (2, lambda d, b: d)):
+        e.recon(At, out, mode, bnum=bnum)
+        got = out.cpu().numpy()
+        for m, b in enumerate((0.7, 1.9)):
+            ref = (Q[m] * f(D[m], b)) @ Q[m].T
+            assert _rel(got[m], ref) < 1e-12, (mode, m)
+            assert np.array_equal(got[m], got[m].T), "reconstruction must be exactly symmetric"
+
+
+# --------------------------------------------------------------------------------------------
+# prox kernels through the C ABI vs golden / oracle
+# --------------------------------------------------------------------------------------------
+def _ctrl(dev, rho=1.0, n=1):
+    from gglasso_b200._lib import CTRL_STRIDE
+    c = np.zeros((n, CTRL_STRIDE))
+    c[:, 0] = rho
+    c[:, 1] = 1.0
+    return torch.from_numpy(c).to(dev)
+
+
+@pytest.mark.parametrize("reg", ["GGL", "FGL"])
+def test_prox_mgl_kernel_vs_reference_fixture(golden, reg):
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import to_dev, _p
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    g = golden("prox_units")
+    Xin = g["X"]
+    K, p, _ = Xin.shape
+    want = g["prox_p_ggl" if reg == "GGL" else "prox_p_fgl"]
+    # latent-mode call: Theta = prox(Omega + L + X) with Omega = Xin, L = X = 0
+    Om, Z = to_dev(Xin, dev), torch.zeros((K, p, p), dtype=torch.float64, device=dev)
+    Th, C = torch.empty_like(Om), torch.empty_like(Om)
+    rc = lib.gg_prox_mgl(_p(Om), _p(Om), _p(Z), _p(Z), _p(Th), _p(C), _p(_ctrl(dev)), float(g["l1"]), float(g["l2"]),
+                         0 if reg == "GGL" else 1, K, p, None, 0)
+    assert rc == 0
+    got = Th.cpu().numpy()
+    if reg == "FGL":
+        assert np.array_equal(got, want)           # TV scan + soft threshold: bit exact
+    else:
+        assert np.abs(got - want).max() < 1e-15    # dnrm2 vs sqrt(sum) can differ in the last bit
+    assert np.array_equal(C.cpu().numpy(), got - 0.0 - Xin)
+
+
+@pytest.mark.parametrize("reg,K,p", [("GGL", 2, 16), ("FGL", 5, 33), ("GGL", 20, 70), ("FGL", 20, 70), ("FGL", 31, 17)])
+def test_prox_mgl_fused_dual_and_norms(reg, K, p):
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import to_dev, _p
+    from oracle import admm_oracle as orc
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(K * 100 + p)
+    Om = np.stack([_sym(rng, p, 0.3) for _ in range(K)])
+    Omp = np.stack([_sym(rng, p, 0.3) for _ in range(K)])
+    X = np.stack([_sym(rng, p, 0.2) for _ in range(K)])
+    rho, l1, l2 = 2.0, 0.21, 0.13
+    want = orc.prox_p(Om + X, l1 / rho, l2 / rho, reg)
+    Xn = X + (Om - want)
+    nt = lib.gg_mgl_ntile(p)
+    parts = torch.zeros((nt * nt, 5), dtype=torch.float64, device=dev)
+    dOm, dOmp, dX = to_dev(Om, dev), to_dev(Omp, dev), to_dev(X, dev)
+    Th = torch.empty_like(dOm)
+    rc = lib.gg_prox_mgl(_p(dOm), _p(dOmp), None, _p(dX), _p(Th), None, _p(_ctrl(dev, rho)), l1, l2,
+                         0 if reg == "GGL" else 1, K, p, _p(parts), 0)
+    assert rc == 0
+    got = Th.cpu().numpy()
+    assert np.abs(got - want).max() < 1e-15
+    assert np.array_equal(got != 0, want != 0)
+    assert np.array_equal(got, got.transpose(0, 2, 1))
+    assert np.abs(dX.cpu().numpy() - Xn).max() < 1e-15
+    sums = parts.sum(0).cpu().numpy()
+    ref = [np.sum(Om ** 2), np.sum(want ** 2), np.sum(Xn ** 2), np.sum((Om - want) ** 2), np.sum((Om - Omp) ** 2)]
+    np.testing.assert_allclose(sums, ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("p,masked", [(1, False), (7, False), (100, True), (257, False)])
+def test_prox_sgl_kernel(p, masked):
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import to_dev, _p
+    from oracle import admm_oracle as orc
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(p)
+    M = 3
+    Om, Omp, X = (np.stack([_sym(rng, p, 0.4) for _ in range(M)]) for _ in range(3))
+    rhos = np.array([1.0, 0.5, 4.0])
+    lam = 0.17
+    mask = np.abs(np.stack([_sym(rng, p) for _ in range(M)])) if masked else None
+    ctrl = _ctrl(dev, 1.0, M)
+    ctrl[:, 0] = torch.from_numpy(rhos).to(dev)
+    n = lib.gg_sgl_nparts(p, M)
+    parts = torch.zeros((M, n, 5), dtype=torch.float64, device=dev)
+    dOm, dOmp, dX = to_dev(Om, dev), to_dev(Omp, dev), to_dev(X, dev)
+    Th = torch.empty_like(dOm)
+    lam_mat = to_dev(lam * mask, dev) if masked else None
+    assert lib.gg_prox_sgl(_p(dOm), _p(dOmp), None, _p(dX), _p(Th), None, _p(ctrl), lam, _p(lam_mat), M, p,
+                           _p(parts), 0) == 0
+    got, gotX = Th.cpu().numpy(), dX.cpu().numpy()
+    sums = parts.sum(1).cpu().numpy()
+    for m in range(M):
+        l = (1 / rhos[m]) * (lam * mask[m] if masked else lam)
+        want = orc.prox_od_1norm(Om[m] + X[m], l)
+        assert np.array_equal(got[m], want)
+        Xn = X[m] + Om[m] - want
+        assert np.array_equal(gotX[m], Xn)
+        ref = [np.sum(Om[m] ** 2), np.sum(want ** 2), np.sum(Xn ** 2), np.sum((Om[m] - want) ** 2),
+               np.sum((Om[m] - Omp[m]) ** 2)]
+        np.testing.assert_allclose(sums[m], ref, rtol=1e-12)
+
+
+# --------------------------------------------------------------------------------------------
+# full solvers vs the real reference (golden fixtures) and vs the oracle, per iteration
+# --------------------------------------------------------------------------------------------
+def _check_hist(info_hist, traj):
+    n = traj.shape[0]
+    h = info_hist[:n]
+    assert np.array_equal(h[:, 4], traj[:, 0]), "rho sequence differs from the reference"
+    np.testing.assert_allclose(h[:, :4], traj[:, 1:5], rtol=1e-7, atol=1e-12)
+
+
+MGL_CASES = ["mgl_ggl_K3_p50", "mgl_ggl_latent_K3_p50", "mgl_fgl_K3_p50", "mgl_fgl_latent_K3_p50",
+             "mgl_ggl_K3_p50_maxiter2", "mgl_ggl_K3_p50_fixedrho", "mgl_ggl_K3_p50_nsamples",
+             "cfg2_ggl", "cfg2_ggl_latent", "cfg2_fgl_tv"]
+
+
+@pytest.mark.parametrize("name", MGL_CASES)
+def test_admm_mgl_vs_reference_golden(golden, name):
+    from gglasso_b200 import ADMM_MGL
+    g = golden(name)
+    S = g["S"]
+    K, p, _ = S.shape
+    kw = dict(ast.literal_eval(str(g["kw"])))
+    (sol, info), out = _quiet(ADMM_MGL, S, float(g["lambda1"]), float(g["lambda2"]), str(g["reg"]),
+                              np.repeat(np.eye(p)[None], K, 0), measure=True, **kw)
+    n = g["traj"].shape[0]
+    assert info["status"] == str(g["status"])
+    assert f"ADMM terminated after {n} iterations with status: {info['status']}." in out
+    assert len(info["residual"]) == n == len(info["runtime"]) == len(info["objective"])
+    np.testing.assert_allclose(info["residual"], g["residual"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(info["objective"], g["objective"], rtol=1e-6)
+    assert _rel(sol["Theta"], g["Theta"]) < PER_ITER_TOL
+    assert np.array_equal(sol["Theta"] != 0, g["Theta"] != 0), "sparsity pattern differs from the reference"
+    assert set(sol) == {"Omega", "Theta", "L", "X"}
+    if "Omega" in g.files:
+        for k in ("Omega", "X", "L"):
+            assert np.linalg.norm(sol[k] - g[k]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(g[k])), k
+
+
+@pytest.mark.parametrize("reg,latent", [("GGL", False), ("FGL", False), ("GGL", True), ("FGL", True)])
+def test_admm_mgl_per_iteration_trajectory_vs_oracle(golden, reg, latent):
+    """first 50 iterations: Omega/Theta/L/X within 1e-8 relative Frobenius of the CPU oracle, same rho path."""
+    from gglasso_b200._engine import run_admm
+    from oracle import admm_oracle as orc
+    g = golden("mgl_ggl_K3_p50")
+    S = g["S"]
+    K, p, _ = S.shape
+    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    kw = dict(tol=1e-9, rtol=1e-9, max_iter=50)
+    otrace = []
+    orc.admm_mgl(S, 0.05, 0.01, reg, Om0, latent=latent, mu1=0.1 if latent else None, trace=otrace, **kw)
+    trace = []
+    st, res = run_admm("mgl", S, Om0, Om0, np.zeros_like(S), lambda1=0.05, lambda2=0.01, reg=reg, latent=latent,
+                       mu=0.1 * np.ones(K) if latent else None, trace=trace, check_every=1, **kw)
+    assert len(trace) == len(otrace)
+    for t, (a, b) in enumerate(zip(trace, otrace)):
+        for k in ("Omega", "Theta", "X") + (("L",) if latent else ()):
+            assert np.linalg.norm(a[k] - b[k]) <= PER_ITER_TOL * max(np.linalg.norm(b[k]), 1e-3), (t, k)
+        assert np.array_equal(a["Theta"] != 0, b["Theta"] != 0), t
+    h = res["hist"][0][:len(otrace)]
+    assert np.array_equal(h[:, 4], np.array([t["rho"] for t in otrace]))
+
+
+SGL_CASES = ["cfg1_sgl", "cfg1_sgl_latent", "cfg1_sgl_mask"]
+
+
+@pytest.mark.parametrize("name", SGL_CASES)
+def test_admm_sgl_vs_reference_golden(golden, name):
+    from gglasso_b200 import ADMM_SGL
+    g = golden(name)
+    S = g["S"]
+    p = S.shape[0]
+    kw = dict(tol=1e-7, rtol=1e-7)
+    if "latent" in name:
+        kw.update(latent=True, mu1=0.1)
+    if "mask" in name:
+        kw["lambda1_mask"] = g["lambda1_mask"]
+    (sol, info), out = _quiet(ADMM_SGL, S, float(g["lambda1"]), np.eye(p), measure=True, **kw)
+    n = g["traj"].shape[0]
+    assert info["status"] == str(g["status"]) and len(info["residual"]) == n
+    assert f"ADMM terminated after {n} iterations" in out
+    np.testing.assert_allclose(info["residual"], g["residual"], rtol=1e-7, atol=1e-12)
+    assert ("L" in sol) == ("latent" in name) and "objective" not in info
+    for k in ("Theta", "Omega", "X") + (("L",) if "L" in sol else ()):
+        assert np.linalg.norm(sol[k] - g[k]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(g[k])), k
+    assert np.array_equal(sol["Theta"] != 0, g["Theta"] != 0)
+
+
+def test_kkt_criterion_vs_reference_golden(golden):
+    from gglasso_b200 import ADMM_MGL, ADMM_SGL
+    g = golden("mgl_fgl_K3_p50_kkt")
+    S = g["S"]
+    K, p, _ = S.shape
+    (sol, info), _ = _quiet(ADMM_MGL, S, 0.05, 0.01, "FGL", np.repeat(np.eye(p)[None], K, 0), tol=1e-5,
+                            stopping_criterion="kkt", update_rho=False, measure=True)
+    assert info["status"] == str(g["status"]) and len(info["residual"]) == len(g["residual"])
+    np.testing.assert_allclose(info["residual"], g["residual"], rtol=1e-6, atol=1e-12)
+    assert _rel(sol["Theta"], g["Theta"]) < PER_ITER_TOL
+    g = golden("cfg1_sgl_kkt")
+    S = g["S"]
+    (sol, info), _ = _quiet(ADMM_SGL, S, 0.05, np.eye(S.shape[0]), tol=1e-6, stopping_criterion="kkt", max_iter=200,
+                            measure=True)
+    assert info["status"] == str(g["status"]) and len(info["residual"]) == len(g["residual"])
+    assert _rel(sol["Theta"], g["Theta"]) < PER_ITER_TOL
+
+
+def test_block_sgl_vs_reference_golden(golden):
+    from gglasso_b200 import block_SGL, get_connected_components
+    g = golden("block_sgl_p100")
+    S, lam = g["S"], float(g["lambda1"])
+    numC, _ = get_connected_components(S, lam)
+    assert numC == int(g["numC"])
+    sol, _ = _quiet(block_SGL, S, lam, np.eye(S.shape[0]), tol=1e-9, rtol=1e-9)
+    assert set(sol) == {"Omega", "Theta", "X"}
+    for k in ("Theta", "Omega", "X"):
+        assert np.linalg.norm(sol[k] - g[k]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(g[k])), k
+    assert np.array_equal(sol["Theta"] != 0, g["Theta"] != 0)
+
+
+def test_mask_of_zeros_gives_inverse():
+    """known-answer test of the reference (tests/test_solvers.py:191-246)."""
+    from gglasso_b200 import ADMM_SGL
+    rng = np.random.default_rng(0)
+    p = 30
+    A = rng.standard_normal((4 * p, p))
+    S = A.T @ A / (4 * p)
+    (sol, info), _ = _quiet(ADMM_SGL, S, 0.1, np.eye(p), tol=1e-10, rtol=1e-10, lambda1_mask=np.zeros((p, p)))
+    np.testing.assert_allclose(sol["Theta"], np.linalg.inv(S), atol=1e-4)
+
+
+@pytest.mark.parametrize("reg,K,p", [("GGL", 4, 200), ("FGL", 3, 333)])
+def test_admm_mgl_block_eigh_path_vs_oracle(reg, K, p):
+    """p > 160 exercises the block-Jacobi (DMMA) eigensolver inside the loop."""
+    from gglasso_b200 import ADMM_MGL
+    from gglasso_b200.datagen import synthetic_mgl
+    from oracle import admm_oracle as orc
+    S = synthetic_mgl(K, p, N=2 * p, seed=3)
+    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    (sol, info), _ = _quiet(ADMM_MGL, S, 0.05, 0.02, reg, Om0, tol=1e-7, rtol=1e-7, measure=True)
+    ref, rinfo = orc.admm_mgl(S, 0.05, 0.02, reg, Om0, tol=1e-7, rtol=1e-7, measure=True)
+    assert info["status"] == rinfo["status"] and len(info["residual"]) == rinfo["iterations"]
+    for k in ("Omega", "Theta", "X"):
+        assert _rel(sol[k], ref[k]) < PER_ITER_TOL, k
+    assert np.array_equal(sol["Theta"] != 0, ref["Theta"] != 0)
+    assert abs(info["objective"][-1] - rinfo["objective"][-1]) <= 1e-6 * abs(rinfo["objective"][-1])
+
+
+def test_input_validation_matches_reference():
+    from gglasso_b200 import ADMM_MGL, ADMM_SGL
+    S = np.repeat(np.eye(4)[None], 2, 0)
+    with pytest.raises(AssertionError):
+        ADMM_MGL(S, 0.1, 0.1, "XYZ", S)
+    with pytest.raises(AssertionError):
+        ADMM_MGL(S, -0.1, 0.1, "GGL", S)
+    with pytest.raises(AssertionError):
+        ADMM_SGL(np.eye(4), 0.1, np.eye(5))
+    with pytest.raises(AssertionError):
+        ADMM_SGL(np.eye(4), 0.1, np.eye(4), latent=True)
