@@ -73,10 +73,11 @@ class Eigh:
         return out
 
 
-def eigh(A):
+def eigh(A, nb2=None):
     """Public helper: batched symmetric eigendecomposition of (M,p,p) / (p,p) numpy input on the GPU.
 
     Returns (D ascending, Q with eigenvectors as columns) like np.linalg.eigh.
+    ``nb2`` in {32, 64, 128} forces the block-Jacobi path for p > 160 (default: tridiagonal D&C path).
     """
     dev = require_cuda()
     A = np.asarray(A, dtype=np.float64)
@@ -84,6 +85,8 @@ def eigh(A):
     At = to_dev(A[None] if single else A, dev)
     M, p, _ = At.shape
     e = Eigh(M, p, dev)
+    if nb2 is not None:
+        e.nb2 = nb2
     D = e.eigh(At, stream=torch.cuda.current_stream().cuda_stream)
     D, order = torch.sort(D, dim=1)
     Vt = torch.gather(At, 1, order[:, :, None].expand(M, p, p))

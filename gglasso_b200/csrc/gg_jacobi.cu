@@ -16,76 +16,10 @@
 //                       H = P P^T over the 2b rows of the pair on FP64 tensor cores (DMMA m8n8k4),
 //                       eigenvectors U of H by the same shared-memory Jacobi, P <- U^T P by DMMA.
 #include "gg_common.cuh"
+#include "gg_jacobi_dev.cuh"
 
 #define GG_SMALL_MAX 160
 #define JS_THREADS 512
-
-// ---- round-robin tournament: n even, round r in [0,n-1), slot s in [0,n/2) -------------------
-__device__ __forceinline__ void rr_pair(int n, int r, int s, int& a, int& b)
-{
-    const int m = n - 1;
-    if (s == 0) { a = m; b = r; }
-    else { a = (r + s) % m; b = (r - s + m) % m; }
-}
-
-// ---- shared-memory one-sided Jacobi on the rows of G (n x n, row stride ld) --------------------
-// LP lanes cooperate on one row pair.  Returns the number of sweeps executed.
-template <int LP>
-__device__ int jacobi_rows_smem(double* G, int n, int ld, double tol, int max_sweeps)
-{
-    const int nn = n + (n & 1);
-    const int half = nn >> 1;
-    const int ngroups = blockDim.x / LP;
-    const int gid = threadIdx.x / LP, gl = threadIdx.x % LP;
-    int sweep = 0;
-    for (; sweep < max_sweeps; ++sweep) {
-        int rot = 0;
-        for (int r = 0; r < nn - 1; ++r) {
-            for (int s0 = 0; s0 < half; s0 += ngroups) {
-                const int s = s0 + gid;
-                bool act = s < half;
-                int i = 0, j = 0;
-                if (act) {
-                    rr_pair(nn, r, s, i, j);
-                    if (i > j) { const int t = i; i = j; j = t; }
-                    act = j < n;
-                }
-                double a = 0.0, b = 0.0, g = 0.0;
-                if (act) {
-                    const double* gi = G + (size_t)i * ld;
-                    const double* gj = G + (size_t)j * ld;
-                    for (int e = gl; e < n; e += LP) {
-                        const double x = gi[e], y = gj[e];
-                        a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
-                    }
-                }
-#pragma unroll
-                for (int o = LP >> 1; o > 0; o >>= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    b += __shfl_xor_sync(0xffffffffu, b, o);
-                    g += __shfl_xor_sync(0xffffffffu, g, o);
-                }
-                if (act && fabs(g) > tol * sqrt(a * b)) {
-                    const double zeta = (b - a) / (2.0 * g);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = rsqrt(1.0 + t * t);
-                    const double sn = c * t;
-                    double* gi = G + (size_t)i * ld;
-                    double* gj = G + (size_t)j * ld;
-                    for (int e = gl; e < n; e += LP) {
-                        const double x = gi[e], y = gj[e];
-                        gi[e] = c * x - sn * y;
-                        gj[e] = sn * x + c * y;
-                    }
-                    rot = 1;
-                }
-            }
-            __syncthreads();
-        }
-        if (__syncthreads_count(rot) == 0) { ++sweep; break; }
-    }
-    return sweep;
-}
 
 // ==========================================================================================
 // small path: one CTA per matrix, everything in shared memory
@@ -438,7 +372,11 @@ bj_finalize_kernel(double* __restrict__ G, double* __restrict__ D, int p, BjStat
 // ==========================================================================================
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-size_t gg_eigh_ws_bytes(int M, int p)
+size_t gg_tridiag_ws_bytes(int M, int n);
+int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl, int mpp, void* wsp, size_t ws_bytes,
+                         cudaStream_t s);
+
+static size_t gg_jacobi_ws_bytes(int M, int p)
 {
     size_t b = 0;
     b += align_up(sizeof(double) * (size_t)M, 256);              // sigma
@@ -448,6 +386,13 @@ size_t gg_eigh_ws_bytes(int M, int p)
     b += 256;                                                    // flags
     b += align_up(sizeof(int) * (size_t)M, 256);                 // sweeps (small path)
     return b;
+}
+
+size_t gg_eigh_ws_bytes(int M, int p)
+{
+    const size_t a = gg_jacobi_ws_bytes(M, p);
+    const size_t b = (p > GG_SMALL_MAX) ? gg_tridiag_ws_bytes(M, p) : 0;
+    return a > b ? a : b;
 }
 
 template <int NB2, int KC>
@@ -479,7 +424,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
                  cudaStream_t s)
 {
     if (M <= 0 || p <= 0) return 0;
-    if (ws_bytes < gg_eigh_ws_bytes(M, p)) return -3;
+    if (ws_bytes < gg_jacobi_ws_bytes(M, p)) return -3;
     char* w = (char*)ws;
     BjState st;
     st.sigma = (double*)w; w += align_up(sizeof(double) * (size_t)M, 256);
@@ -510,9 +455,13 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
         return 0;
     }
 
-    // ---- block path ----
+    // ---- large p: tridiagonalisation + divide & conquer (default), or block Jacobi on request ----
+    if (block_nb2 != 32 && block_nb2 != 64 && block_nb2 != 128) {
+        const int rc = gg_eigh_tridiag_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, s);
+        if (info) info[0] = -1;
+        return rc;
+    }
     int nb2 = block_nb2;
-    if (nb2 != 32 && nb2 != 64 && nb2 != 128) nb2 = 64;
     const int b = nb2 / 2;
     const int nb = (p + b - 1) / b;
     const int nbe = nb + (nb & 1);

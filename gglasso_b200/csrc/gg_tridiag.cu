@@ -1,0 +1,919 @@
+// gg_tridiag.cu -- large-p symmetric eigensolver: Householder tridiagonalisation, tridiagonal
+// divide & conquer, blocked back-transformation (sm_100a).  Batched over M matrices.
+//
+// Replaces np.linalg.eigh (LAPACK dsyevd) at admm_solver.py:181,199 / single_admm_solver.py:164,174
+// for p > GG_SMALL_MAX.  Same three stages as dsyevd (dsytrd, dstedc, dormtr), laid out for the GPU:
+//
+//   1. sytrd   A = Q_H T Q_H^T.  Per column j two launches over the whole batch:
+//              tr_col_kernel (one CTA per matrix: finish w_{j-1}, form the Householder vector v_j from
+//              the already updated row j) and tr_symv_kernel (streams the trailing matrix once: applies
+//              the pending rank-2 update of step j-1 and accumulates y_j = A v_j in the same pass).
+//   2. stedc   Cuppen divide & conquer with Gu/Eisenstat's stable eigenvector formula: rank-one tearing
+//              at every split, leaves (<=32) by the shared-memory Jacobi kernel, then level-synchronous
+//              merges: deflation (dc_prepare), secular equation (dc_secular, one warp per root),
+//              Loewner z-hat (dc_zhat), eigenvectors of the rank-one update (dc_vectors) and the basis
+//              update Qt_new = U^T Qt on FP64 tensor cores (dc_gemm, DMMA).
+//   3. ormtr   Vt <- Vt Q_H^T with compact-WY panels (bt_larft_kernel, bt_apply_kernel, DMMA); every CTA owns a
+//              band of rows and walks all panels, so the whole back-transformation is one launch.
+//
+// Eigenvectors are returned as rows (Vt), order arbitrary -- only V f(D) V^T is consumed downstream.
+#include "gg_common.cuh"
+#include "gg_jacobi_dev.cuh"
+#include <stdlib.h>
+
+#define TR_EPS 2.220446049250313e-16
+#define DC_LEAF 32
+#define BT_NB 32
+#define BT_R 32
+
+
+// =============================================================================================
+// stage 1: tridiagonalisation
+// =============================================================================================
+struct TrWs {
+    double* Vh;      // (M,n,n) row j = Householder vector v_j (global indexing, v_j[j+1] = 1)
+    double* tau;     // (M,n)
+    double* d;       // (M,n)
+    double* e;       // (M,n)
+    double* vbuf;    // (M,2,n)
+    double* w;       // (M,n)
+    double* y;       // (M,n)
+};
+
+// One CTA per matrix.  j in [0, n-1].
+__global__ void __launch_bounds__(1024)
+tr_col_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip)
+{
+    __shared__ double red[64];
+    __shared__ double s_bc[4];
+    const int m = blockIdx.x;
+    if (skip && skip[m]) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* Am = A + (size_t)m * n * n;
+    double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;    // v^{(j-1)}
+    double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n;           // v^{(j)}
+    double* w = ws.w + (size_t)m * n;
+    const double* y = ws.y + (size_t)m * n;
+    double* tau = ws.tau + (size_t)m * n;
+
+    double wj = 0.0;
+    if (j >= 1) {
+        // finish w^{(j-1)} = p + alpha v, p = tau*y, alpha = -tau/2 * (p.v), on indices j..n-1
+        const double tp = tau[j - 1];
+        double part[1] = {0.0};
+        for (int i = j + tid; i < n; i += nt) part[0] += (tp * y[i]) * vprev[i];
+        gg_block_sum<1>(part, red);
+        if (tid == 0) s_bc[0] = -0.5 * tp * part[0];
+        __syncthreads();
+        const double alpha = s_bc[0];
+        for (int i = j + tid; i < n; i += nt) w[i] = tp * y[i] + alpha * vprev[i];
+        __syncthreads();
+        wj = w[j];                                   // v^{(j-1)}[j] = 1
+    }
+    // row j (== column j) of the trailing block, with the pending update of step j-1 applied
+    // a_i = A[j][i] - v_i w_j - w_i v_j ,  i in j..n-1
+    double* rowj = Am + (size_t)j * n;
+    double part[1] = {0.0};
+    for (int i = j + tid; i < n; i += nt) {
+        double a = rowj[i];
+        if (j >= 1) a = a - vprev[i] * wj - w[i];    // v_j = 1
+        rowj[i] = a;
+        if (i >= j + 2) part[0] += a * a;
+    }
+    gg_block_sum<1>(part, red);
+    __syncthreads();
+    if (tid == 0) {
+        ws.d[(size_t)m * n + j] = rowj[j];
+        if (j < n - 1) {
+            const double alpha = rowj[j + 1];
+            const double xn2 = part[0];
+            double t = 0.0, beta = alpha, scale = 0.0;
+            if (xn2 > 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                t = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            tau[j] = t;
+            ws.e[(size_t)m * n + j] = beta;
+            s_bc[1] = scale;
+        }
+    }
+    __syncthreads();
+    if (j < n - 1) {
+        const double scale = s_bc[1];
+        double* vh = ws.Vh + (size_t)m * n * n + (size_t)j * n;
+        for (int i = j + 1 + tid; i < n; i += nt) {
+            const double v = (i == j + 1) ? 1.0 : rowj[i] * scale;
+            vcur[i] = v;
+            vh[i] = v;
+        }
+    }
+}
+
+// Streams the trailing block rows i in (j, n): a_ik -= vp_i w_k + w_i vp_k (pending step j-1), then
+// y_i = sum_k a_ik v_k.  Full symmetric storage: every row is complete, no atomics.
+#define SV_ROWS 32
+__global__ void __launch_bounds__(256)
+tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip)
+{
+    extern __shared__ double sv[];           // vp[t], w[t], v[t]
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    const int t = n - j - 1;
+    const int base = j + 1;
+    double* s_vp = sv;
+    double* s_w = sv + t;
+    double* s_v = sv + 2 * t;
+    const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;
+    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n;
+    const double* w = ws.w + (size_t)m * n;
+    const bool pend = (j >= 1);
+    for (int k = threadIdx.x; k < t; k += 256) {
+        s_vp[k] = pend ? vprev[base + k] : 0.0;
+        s_w[k] = pend ? w[base + k] : 0.0;
+        s_v[k] = vcur[base + k];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* Am = A + (size_t)m * n * n;
+    double* y = ws.y + (size_t)m * n;
+    for (int r = wid; r < SV_ROWS; r += 8) {
+        const int il = blockIdx.x * SV_ROWS + r;      // local row
+        if (il >= t) break;
+        double* row = Am + (size_t)(base + il) * n + base;
+        const double vpi = s_vp[il], wi = s_w[il];
+        double acc = 0.0;
+        if (pend) {
+            for (int k = lane; k < t; k += 32) {
+                double a = row[k];
+                a = a - vpi * s_w[k] - wi * s_vp[k];
+                row[k] = a;
+                acc = fma(a, s_v[k], acc);
+            }
+        } else {
+            for (int k = lane; k < t; k += 32) acc = fma(row[k], s_v[k], acc);
+        }
+        acc = gg_warp_sum(acc);
+        if (lane == 0) y[base + il] = acc;
+    }
+}
+
+// =============================================================================================
+// stage 2: divide & conquer on the tridiagonal matrices
+// =============================================================================================
+struct DcWs {
+    double* lam[2];   // (M,n) eigenvalues, ping-pong
+    double* z;        // (M,n)
+    double* dl;       // (M,n) non-deflated poles (ascending) per node
+    double* wnd;      // (M,n) their z components
+    double* zhat;     // (M,n)
+    int* ndrow;       // (M,n) global row of the i-th non-deflated vector
+    int* nodek;       // (M,nodes_max) number of non-deflated
+    double* noderho;  // (M,nodes_max)
+    double* U;        // (M,n,n) Delta / eigenvector matrices, block diagonal like Qt
+    int nodes_max;
+};
+
+__host__ __device__ __forceinline__ int dc_bnd(int n, int level, int i) { return (int)(((long long)i * n) >> level); }
+
+// normalise T to unit max-norm (as dstedc does) so the deflation tolerance is scale free
+__global__ void __launch_bounds__(256)
+dc_scale_kernel(double* __restrict__ d, double* __restrict__ e, int n, double* __restrict__ scale,
+                const int* __restrict__ skip)
+{
+    __shared__ double red[32];
+    __shared__ double s_inv;
+    const int m = blockIdx.x;
+    if (skip && skip[m]) return;
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        mx = fmax(mx, fabs(d[(size_t)m * n + i]));
+        if (i < n - 1) mx = fmax(mx, fabs(e[(size_t)m * n + i]));
+    }
+    mx = gg_block_max(mx, red);
+    if (threadIdx.x == 0) {
+        if (!(mx > 0.0)) mx = 1.0;
+        scale[m] = mx;
+        s_inv = 1.0 / mx;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        d[(size_t)m * n + i] *= inv;
+        if (i < n - 1) e[(size_t)m * n + i] *= inv;
+    }
+}
+
+__global__ void dc_unscale_kernel(const double* __restrict__ lam, const double* __restrict__ scale, int n,
+                                  double* __restrict__ D, const int* __restrict__ skip)
+{
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    const double s = scale[m];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        D[(size_t)m * n + i] = lam[(size_t)m * n + i] * s;
+}
+
+// subtract |e_s| from both neighbours of every split point (all levels at once)
+__global__ void dc_tear_kernel(double* __restrict__ d, const double* __restrict__ e, int n, int levels,
+                               const int* __restrict__ skip)
+{
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;   // enumerates (level, node)
+    int l = 0, i = t;
+    while (l < levels && i >= (1 << l)) { i -= (1 << l); ++l; }
+    if (l >= levels) return;
+    const int s = dc_bnd(n, l + 1, 2 * i + 1);
+    const double rho = fabs(e[(size_t)m * n + s - 1]);
+    d[(size_t)m * n + s - 1] -= rho;
+    d[(size_t)m * n + s] -= rho;
+}
+
+// leaves: dense (<= DC_LEAF) tridiagonal blocks by shared-memory Jacobi; writes lam, block-diagonal Qt
+__global__ void __launch_bounds__(128)
+dc_leaf_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, int levels,
+               double* __restrict__ lam, double* __restrict__ Qt, const int* __restrict__ skip)
+{
+    __shared__ double G[DC_LEAF * (DC_LEAF + 1)];
+    __shared__ double s_sigma;
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    const int lo = dc_bnd(n, levels, blockIdx.x), hi = dc_bnd(n, levels, blockIdx.x + 1);
+    const int sz = hi - lo, ld = DC_LEAF + 1;
+    const double* dm = d + (size_t)m * n;
+    const double* em = e + (size_t)m * n;
+    for (int idx = threadIdx.x; idx < sz * sz; idx += blockDim.x) {
+        const int r = idx / sz, c = idx % sz;
+        double v = 0.0;
+        if (r == c) v = dm[lo + r];
+        else if (c == r + 1) v = em[lo + r];
+        else if (r == c + 1) v = em[lo + c];
+        G[r * ld + c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double lo_b = 1.0e300, hi_b = -1.0e300;
+        for (int r = 0; r < sz; ++r) {
+            double rs = 0.0;
+            if (r > 0) rs += fabs(G[r * ld + r - 1]);
+            if (r + 1 < sz) rs += fabs(G[r * ld + r + 1]);
+            lo_b = fmin(lo_b, G[r * ld + r] - rs);
+            hi_b = fmax(hi_b, G[r * ld + r] + rs);
+        }
+        const double c = 0.5 * (lo_b + hi_b);
+        double h = 0.5 * (hi_b - lo_b);
+        if (!(h > 0.0)) h = fmax(fabs(c), 1.0);
+        s_sigma = 2.0 * h - c;
+    }
+    __syncthreads();
+    const double sigma = s_sigma;
+    if (threadIdx.x < sz) G[threadIdx.x * ld + threadIdx.x] += sigma;
+    __syncthreads();
+    jacobi_rows_smem<8>(G, sz, ld, 4.0e-15, 40);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = wid; r < sz; r += 4) {
+        const double x = (lane < sz) ? G[r * ld + lane] : 0.0;
+        const double nrm = sqrt(gg_warp_sum(x * x));
+        if (lane == 0) lam[(size_t)m * n + lo + r] = nrm - sigma;
+        if (lane < sz) Qt[(size_t)m * n * n + (size_t)(lo + r) * n + lo + lane] = x / nrm;
+    }
+}
+
+// One CTA per node: z vector, sort, deflation (serial scan by thread 0), Givens rotations on rows,
+// copies of deflated rows/eigenvalues to the output buffers.
+__global__ void __launch_bounds__(1024)
+dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* __restrict__ lam_in,
+                  double* __restrict__ lam_out, double* __restrict__ Qin, double* __restrict__ Qout, DcWs ws,
+                  const int* __restrict__ skip)
+{
+    extern __shared__ double sm[];             // d[N], z[N], then ints idx[N], dfl[N], rots
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    const int node = blockIdx.x;
+    const int lo = dc_bnd(n, level, node), hi = dc_bnd(n, level, node + 1), mid = dc_bnd(n, level + 1, 2 * node + 1);
+    const int N = hi - lo, n1 = mid - lo;
+    double* sd = sm;
+    double* sz = sm + N;
+    double* rc = sm + 2 * N;                   // rotation cos
+    double* rs = sm + 3 * N;                   // rotation sin
+    int* idx = (int*)(sm + 4 * N);
+    int* nd = idx + N;
+    int* df = nd + N;
+    int* rp = df + N;
+    int* rn = rp + N;
+    __shared__ int s_k, s_ndf, s_nrot;
+    __shared__ double s_rho;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* Qm = Qin + (size_t)m * n * n;
+    double* Qo = Qout + (size_t)m * n * n;
+    const double es = e[(size_t)m * n + mid - 1];
+    const double sgn = es >= 0.0 ? 1.0 : -1.0;
+    const double rho = 2.0 * fabs(es);
+    const double isq2 = 0.70710678118654752440;
+    for (int i = tid; i < N; i += nt) {
+        sd[i] = lam_in[(size_t)m * n + lo + i];
+        sz[i] = (i < n1 ? Qm[(size_t)(lo + i) * n + mid - 1] : sgn * Qm[(size_t)(lo + i) * n + mid]) * isq2;
+    }
+    __syncthreads();
+    // rank sort (stable)
+    for (int i = tid; i < N; i += nt) {
+        const double di = sd[i];
+        int r = 0;
+        for (int q = 0; q < N; ++q) {
+            const double dq = sd[q];
+            r += (dq < di || (dq == di && q < i)) ? 1 : 0;
+        }
+        idx[r] = i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double dmax = 0.0, zmax = 0.0;
+        for (int i = 0; i < N; ++i) { dmax = fmax(dmax, fabs(sd[i])); zmax = fmax(zmax, fabs(sz[i])); }
+        const double tol = 8.0 * TR_EPS * fmax(dmax, zmax);
+        int k = 0, ndf = 0, nrot = 0, pj = -1;
+        if (rho * zmax <= tol) {
+            for (int i = 0; i < N; ++i) df[ndf++] = i;
+        } else {
+            for (int t = 0; t < N; ++t) {
+                const int nj = idx[t];
+                if (rho * fabs(sz[nj]) <= tol) { df[ndf++] = nj; continue; }
+                if (pj < 0) { pj = nj; continue; }
+                double s = sz[pj], c = sz[nj];
+                const double tau = hypot(c, s);
+                const double tt = sd[nj] - sd[pj];
+                c /= tau; s = -s / tau;
+                if (fabs(tt * c * s) <= tol) {
+                    sz[nj] = tau; sz[pj] = 0.0;
+                    rp[nrot] = pj; rn[nrot] = nj; rc[nrot] = c; rs[nrot] = s; ++nrot;
+                    const double tnew = sd[pj] * c * c + sd[nj] * s * s;
+                    sd[nj] = sd[pj] * s * s + sd[nj] * c * c;
+                    sd[pj] = tnew;
+                    df[ndf++] = pj;
+                    pj = nj;
+                } else {
+                    nd[k++] = pj;
+                    pj = nj;
+                }
+            }
+            if (pj >= 0) nd[k++] = pj;
+        }
+        s_k = k; s_ndf = ndf; s_nrot = nrot; s_rho = rho;
+        ws.nodek[(size_t)m * ws.nodes_max + node] = k;
+        ws.noderho[(size_t)m * ws.nodes_max + node] = rho;
+    }
+    __syncthreads();
+    const int k = s_k, ndf = s_ndf, nrot = s_nrot;
+    // Givens rotations on row pairs (in order; chains share rows)
+    for (int r = 0; r < nrot; ++r) {
+        double* a = Qm + (size_t)(lo + rp[r]) * n + lo;
+        double* b = Qm + (size_t)(lo + rn[r]) * n + lo;
+        const double c = rc[r], s = rs[r];
+        for (int col = tid; col < N; col += nt) {
+            const double x = a[col], yv = b[col];
+            a[col] = c * x + s * yv;
+            b[col] = -s * x + c * yv;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < k; i += nt) {
+        ws.ndrow[(size_t)m * n + lo + i] = lo + nd[i];
+        ws.dl[(size_t)m * n + lo + i] = sd[nd[i]];
+        ws.wnd[(size_t)m * n + lo + i] = sz[nd[i]];
+    }
+    // deflated eigenpairs go to rows lo+k.. of the output unchanged
+    for (int t = 0; t < ndf; ++t) {
+        const double* src = Qm + (size_t)(lo + df[t]) * n + lo;
+        double* dst = Qo + (size_t)(lo + k + t) * n + lo;
+        for (int col = tid; col < N; col += nt) dst[col] = src[col];
+        if (tid == 0) lam_out[(size_t)m * n + lo + k + t] = sd[df[t]];
+    }
+}
+
+// One warp per root: solves 1 + rho sum w_i^2/(dl_i - lam) = 0 in (dl_j, dl_{j+1}) with the shift to the
+// nearer pole, rational ("middle way") steps safeguarded by bisection; writes Delta[j][i] = dl_i - lam_j.
+__global__ void __launch_bounds__(256)
+dc_secular_kernel(int n, int level, double* __restrict__ lam_out, DcWs ws, const int* __restrict__ skip)
+{
+    extern __shared__ double sm[];           // dl[k], w2[k]
+    const int m = blockIdx.z;
+    if (skip && skip[m]) return;
+    const int node = blockIdx.y;
+    const int k = ws.nodek[(size_t)m * ws.nodes_max + node];
+    if ((int)blockIdx.x * 8 >= k) return;
+    const int lo = dc_bnd(n, level, node);
+    const double rho = ws.noderho[(size_t)m * ws.nodes_max + node];
+    double* sdl = sm;
+    double* sw2 = sm + k;
+    for (int i = threadIdx.x; i < k; i += 256) {
+        sdl[i] = ws.dl[(size_t)m * n + lo + i];
+        const double w = ws.wnd[(size_t)m * n + lo + i];
+        sw2[i] = rho * w * w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = blockIdx.x * 8 + wid;
+    if (j >= k) return;
+    double* Drow = ws.U + (size_t)m * n * n + (size_t)(lo + j) * n + lo;
+    int org;
+    double tau;
+    if (k == 1) {
+        org = 0; tau = sw2[0];
+    } else {
+        const bool last = (j == k - 1);
+        double lb, ub;
+        int ia, ib;
+        if (!last) {
+            const double mid = 0.5 * (sdl[j + 1] - sdl[j]);
+            double f = 0.0;
+            for (int i = lane; i < k; i += 32) f += sw2[i] / ((sdl[i] - sdl[j]) - mid);
+            f = 1.0 + gg_warp_sum(f);
+            if (f >= 0.0) { org = j; lb = 0.0; ub = mid; tau = 0.5 * mid; }
+            else { org = j + 1; lb = -mid; ub = 0.0; tau = -0.5 * mid; }
+            ia = j; ib = j + 1;
+        } else {
+            double span = 0.0;
+            for (int i = lane; i < k; i += 32) span += sw2[i];
+            span = gg_warp_sum(span);
+            org = k - 1; lb = 0.0; ub = span; tau = 0.5 * span; ia = k - 2; ib = k - 1;
+        }
+        const double dorg = sdl[org];
+        const int split = last ? (k - 1) : (j + 1);          // psi: i < split, phi: i >= split
+        for (int it = 0; it < 100; ++it) {
+            double psi = 0.0, phi = 0.0, dpsi = 0.0, dphi = 0.0, sabs = 0.0;
+            for (int i = lane; i < k; i += 32) {
+                const double dlt = (sdl[i] - dorg) - tau;
+                const double t = sw2[i] / dlt;
+                const double dt = t / dlt;
+                if (i < split) { psi += t; dpsi += dt; } else { phi += t; dphi += dt; }
+                sabs += fabs(t);
+            }
+            psi = gg_warp_sum(psi); phi = gg_warp_sum(phi); dpsi = gg_warp_sum(dpsi);
+            dphi = gg_warp_sum(dphi); sabs = gg_warp_sum(sabs);
+            const double f = 1.0 + psi + phi, df = dpsi + dphi;
+            if (fabs(f) <= TR_EPS * (8.0 * sabs + 2.0 + fabs(tau) * df)) break;
+            if (f < 0.0) lb = fmax(lb, tau); else ub = fmin(ub, tau);
+            const double Da = (sdl[ia] - dorg) - tau, Db = (sdl[ib] - dorg) - tau;
+            const double c = f - Da * dpsi - Db * dphi;
+            const double a = (Da + Db) * f - Da * Db * df;
+            const double b = Da * Db * f;
+            double eta = 0.0;
+            bool ok = false;
+            if (c == 0.0) {
+                if (a != 0.0) { eta = b / a; ok = true; }
+            } else {
+                const double disc = a * a - 4.0 * b * c;
+                if (disc >= 0.0) {
+                    const double sq = sqrt(disc);
+                    eta = (a <= 0.0) ? (a - sq) / (2.0 * c) : 2.0 * b / (a + sq);
+                    ok = true;
+                }
+            }
+            if (!ok || !isfinite(eta) || f * eta >= 0.0) eta = -f / df;
+            double nt = tau + eta;
+            if (!(nt > lb && nt < ub)) nt = 0.5 * (lb + ub);
+            if (nt == tau) break;
+            tau = nt;
+            if (ub - lb <= 2.0 * TR_EPS * fmax(fabs(lb), fabs(ub))) break;
+        }
+    }
+    const double dorg = sdl[org];
+    for (int i = lane; i < k; i += 32) Drow[i] = (sdl[i] - dorg) - tau;
+    if (lane == 0) lam_out[(size_t)m * n + lo + j] = dorg + tau;
+}
+
+// Loewner formula: zhat_i = sign(w_i) sqrt(-Delta_ii prod_{j!=i} Delta_ji/(dl_i - dl_j))
+__global__ void __launch_bounds__(256)
+dc_zhat_kernel(int n, int level, DcWs ws, const int* __restrict__ skip)
+{
+    const int m = blockIdx.z;
+    if (skip && skip[m]) return;
+    const int node = blockIdx.y;
+    const int k = ws.nodek[(size_t)m * ws.nodes_max + node];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= k) return;
+    const int lo = dc_bnd(n, level, node);
+    const double* dl = ws.dl + (size_t)m * n + lo;
+    const double* Dm = ws.U + (size_t)m * n * n + (size_t)lo * n + lo;
+    const double di = dl[i];
+    double prod = Dm[(size_t)i * n + i];
+    for (int j = 0; j < k; ++j) {
+        if (j != i) prod *= Dm[(size_t)j * n + i] / (di - dl[j]);
+    }
+    ws.zhat[(size_t)m * n + lo + i] = copysign(sqrt(-prod), ws.wnd[(size_t)m * n + lo + i]);
+}
+
+// U[j][i] = zhat_i / Delta[j][i], rows normalised (row j = eigenvector j of D + rho z z^T)
+__global__ void __launch_bounds__(256)
+dc_vectors_kernel(int n, int level, DcWs ws, const int* __restrict__ skip)
+{
+    const int m = blockIdx.z;
+    if (skip && skip[m]) return;
+    const int node = blockIdx.y;
+    const int k = ws.nodek[(size_t)m * ws.nodes_max + node];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = blockIdx.x * 8 + wid;
+    if (j >= k) return;
+    const int lo = dc_bnd(n, level, node);
+    const double* zh = ws.zhat + (size_t)m * n + lo;
+    double* Drow = ws.U + (size_t)m * n * n + (size_t)(lo + j) * n + lo;
+    double ss = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        const double s = zh[i] / Drow[i];
+        Drow[i] = s;
+        ss = fma(s, s, ss);
+    }
+    ss = gg_warp_sum(ss);
+    const double inv = rsqrt(ss);
+    for (int i = lane; i < k; i += 32) Drow[i] *= inv;
+}
+
+// Qout[lo+j][lo+c] = sum_i U[j][i] Qin[ndrow_i][lo+c]   (j < k, c < N), 64x64 tiles, DMMA
+#define DG_T 64
+#define DG_KC 16
+__global__ void __launch_bounds__(256)
+dc_gemm_kernel(int n, int level, const double* __restrict__ Qin, double* __restrict__ Qout, DcWs ws,
+               const int* __restrict__ skip)
+{
+    __shared__ double As[2][DG_T][DG_KC + 4];       // U tile   [j][i]
+    __shared__ double Bs[2][DG_KC][DG_T + 4];       // Qin tile [i][c]
+    const int m = blockIdx.z / (1 << level), node = blockIdx.z % (1 << level);
+    if (skip && skip[m]) return;
+    const int k = ws.nodek[(size_t)m * ws.nodes_max + node];
+    const int lo = dc_bnd(n, level, node), hi = dc_bnd(n, level, node + 1);
+    const int N = hi - lo;
+    const int j0 = blockIdx.y * DG_T, c0 = blockIdx.x * DG_T;
+    if (j0 >= k || c0 >= N) return;
+    const double* Um = ws.U + (size_t)m * n * n + (size_t)lo * n + lo;
+    const double* Qm = Qin + (size_t)m * n * n;
+    const int* ndrow = ws.ndrow + (size_t)m * n + lo;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int wr = wid >> 1, wc = wid & 1;          // 4 x 2 warps, 16 x 32 outputs each
+    const int nchunks = (k + DG_KC - 1) / DG_KC;
+
+    auto load_chunk = [&](int ch, int buf) {
+        const int i0 = ch * DG_KC;
+        for (int idx = tid; idx < DG_T * DG_KC; idx += 256) {
+            const int jj = idx / DG_KC, ii = idx % DG_KC;
+            double* dst = &As[buf][jj][ii];
+            if (j0 + jj < k && i0 + ii < k) gg_cp_async8(dst, Um + (size_t)(j0 + jj) * n + i0 + ii);
+            else *dst = 0.0;
+        }
+        for (int idx = tid; idx < DG_KC * DG_T; idx += 256) {
+            const int ii = idx / DG_T, cc = idx % DG_T;
+            double* dst = &Bs[buf][ii][cc];
+            if (i0 + ii < k && c0 + cc < N) gg_cp_async8(dst, Qm + (size_t)ndrow[i0 + ii] * n + lo + c0 + cc);
+            else *dst = 0.0;
+        }
+        gg_cp_commit();
+    };
+
+    double acc[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    load_chunk(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) { load_chunk(ch + 1, (ch + 1) & 1); gg_cp_wait<1>(); }
+        else gg_cp_wait<0>();
+        __syncthreads();
+        const int buf = ch & 1;
+#pragma unroll
+        for (int k0 = 0; k0 < DG_KC; k0 += 4) {
+            double fa[2], fb[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) fa[a] = As[buf][(wr * 2 + a) * 8 + fr][k0 + fc];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) fb[b] = Bs[buf][k0 + fc][(wc * 4 + b) * 8 + fr];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) gg_dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+        }
+        __syncthreads();
+    }
+    double* Qo = Qout + (size_t)m * n * n;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int jj = j0 + (wr * 2 + a) * 8 + fr;
+        if (jj < k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int cc = c0 + (wc * 4 + b) * 8 + 2 * fc;
+                double* dst = Qo + (size_t)(lo + jj) * n + lo + cc;
+                if (cc < N) dst[0] = acc[a][b][0];
+                if (cc + 1 < N) dst[1] = acc[a][b][1];
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// stage 3: back-transformation  Vt <- Vt Q_H^T  (compact WY panels of BT_NB reflectors)
+// =============================================================================================
+// T factor of panel b: H_{j0}...H_{j0+nb-1} = I - V T V^T (forward, columnwise; LAPACK dlarft)
+__global__ void __launch_bounds__(256)
+bt_larft_kernel(const double* __restrict__ Vh, const double* __restrict__ tau, int n, double* __restrict__ Tm,
+                int npanels, const int* __restrict__ skip)
+{
+    __shared__ double Gs[BT_NB][BT_NB + 1];
+    __shared__ double Ts[BT_NB][BT_NB + 1];
+    const int m = blockIdx.y, pb = blockIdx.x;
+    if (skip && skip[m]) return;
+    const int j0 = pb * BT_NB;
+    const double* V = Vh + (size_t)m * n * n;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // Gram of the panel's reflectors (rows of Vh), entries a <= b only
+    for (int pr = wid; pr < BT_NB * BT_NB; pr += 8) {
+        const int a = pr / BT_NB, b = pr % BT_NB;
+        if (a > b) continue;
+        const int ja = j0 + a, jb = j0 + b;
+        double s = 0.0;
+        if (ja < n - 1 && jb < n - 1) {
+            const double* va = V + (size_t)ja * n;
+            const double* vb = V + (size_t)jb * n;
+            for (int i = jb + 1 + lane; i < n; i += 32) s = fma(va[i], vb[i], s);
+        }
+        s = gg_warp_sum(s);
+        if (lane == 0) Gs[a][b] = s;
+    }
+    for (int idx = threadIdx.x; idx < BT_NB * BT_NB; idx += 256) Ts[idx / BT_NB][idx % BT_NB] = 0.0;
+    __syncthreads();
+    // column recurrence: T[0:i,i] = -tau_i T[0:i,0:i] G[0:i,i]
+    for (int i = 0; i < BT_NB; ++i) {
+        const int ji = j0 + i;
+        const double ti = (ji < n - 1) ? tau[(size_t)m * n + ji] : 0.0;
+        if (threadIdx.x < i) {
+            const int r = threadIdx.x;
+            double s = 0.0;
+            for (int c = r; c < i; ++c) s = fma(Ts[r][c], Gs[c][i], s);
+            Ts[r][i] = -ti * s;
+        }
+        if (threadIdx.x == 0) Ts[i][i] = ti;
+        __syncthreads();
+    }
+    double* To = Tm + ((size_t)m * npanels + pb) * BT_NB * BT_NB;
+    for (int idx = threadIdx.x; idx < BT_NB * BT_NB; idx += 256) To[idx] = Ts[idx / BT_NB][idx % BT_NB];
+}
+
+// Each CTA owns BT_R rows of Q (row-major, n columns) and applies all panels, last to first:
+//   Y = Band V_b ; Y <- Y T_b^T ; Band <- Band - Y V_b^T
+#define BT_KC 32
+__global__ void __launch_bounds__(256)
+bt_apply_kernel(double* __restrict__ Q, const double* __restrict__ Vh, const double* __restrict__ Tm, int n,
+                int npanels, const int* __restrict__ skip)
+{
+    __shared__ double Bt[BT_R][BT_KC + 4];       // band tile   [r][i]
+    __shared__ double Vt_[BT_NB][BT_KC + 4];     // panel tile  [jj][i]
+    __shared__ double Ys[BT_R][BT_NB + 4];
+    __shared__ double Y2[BT_R][BT_NB + 4];
+    __shared__ double Tsm[BT_NB][BT_NB + 1];
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    const int r0 = blockIdx.x * BT_R;
+    double* Qm = Q + (size_t)m * n * n;
+    const double* V = Vh + (size_t)m * n * n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    // 4x4 output tiles of 8x8 over 8 warps: warp -> tile row (wid>>1), tile cols (wid&1)*2 + {0,1}
+    const int tr = wid >> 1, tc0 = (wid & 1) * 2;
+
+    for (int pb = npanels - 1; pb >= 0; --pb) {
+        const int j0 = pb * BT_NB;
+        const int istart = ((j0 + 1) / BT_KC) * BT_KC;        // reflectors of this panel vanish below j0+1
+        const double* Tg = Tm + ((size_t)m * npanels + pb) * BT_NB * BT_NB;
+        for (int idx = tid; idx < BT_NB * BT_NB; idx += 256) Tsm[idx / BT_NB][idx % BT_NB] = Tg[idx];
+        // ---- Y = Band V_b ------------------------------------------------------------------
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int i0 = istart; i0 < n; i0 += BT_KC) {
+            for (int idx = tid; idx < BT_R * BT_KC; idx += 256) {
+                const int r = idx / BT_KC, ii = idx % BT_KC;
+                const int gr = r0 + r, gi = i0 + ii;
+                Bt[r][ii] = (gr < n && gi < n) ? Qm[(size_t)gr * n + gi] : 0.0;
+                const int gj = j0 + r;                      // BT_R == BT_NB
+                Vt_[r][ii] = (gj < n - 1 && gi < n) ? V[(size_t)gj * n + gi] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k0 = 0; k0 < BT_KC; k0 += 4) {
+                const double fa = Bt[tr * 8 + fr][k0 + fc];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const double fb = Vt_[(tc0 + b) * 8 + fr][k0 + fc];
+                    gg_dmma(acc[b][0], acc[b][1], fa, fb);
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            Ys[tr * 8 + fr][(tc0 + b) * 8 + 2 * fc] = acc[b][0];
+            Ys[tr * 8 + fr][(tc0 + b) * 8 + 2 * fc + 1] = acc[b][1];
+        }
+        __syncthreads();
+        // ---- Y2 = Y T^T :  Y2[r][a] = sum_b Y[r][b] T[a][b]  (T upper triangular: b >= a) -------
+        for (int idx = tid; idx < BT_R * BT_NB; idx += 256) {
+            const int r = idx / BT_NB, a = idx % BT_NB;
+            double s = 0.0;
+            for (int b = a; b < BT_NB; ++b) s = fma(Ys[r][b], Tsm[a][b], s);
+            Y2[r][a] = s;
+        }
+        __syncthreads();
+        // ---- Band -= Y2 V_b^T -------------------------------------------------------------------
+        for (int i0 = istart; i0 < n; i0 += BT_KC) {
+            for (int idx = tid; idx < BT_NB * BT_KC; idx += 256) {
+                const int jj = idx / BT_KC, ii = idx % BT_KC;
+                const int gj = j0 + jj, gi = i0 + ii;
+                Vt_[jj][ii] = (gj < n - 1 && gi < n) ? V[(size_t)gj * n + gi] : 0.0;
+            }
+            __syncthreads();
+            // output tile: BT_R x BT_KC = 4 x 4 tiles of 8x8; warp -> row tile tr, col tiles tc0 + {0,1}
+            double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int k0 = 0; k0 < BT_NB; k0 += 4) {
+                const double fa = Y2[tr * 8 + fr][k0 + fc];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const double fb = Vt_[k0 + fc][(tc0 + b) * 8 + fr];
+                    gg_dmma(o[b][0], o[b][1], fa, fb);
+                }
+            }
+            const int gr = r0 + tr * 8 + fr;
+            if (gr < n) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int gi = i0 + (tc0 + b) * 8 + 2 * fc;
+                    double* dst = Qm + (size_t)gr * n + gi;
+                    if (gi < n) dst[0] -= o[b][0];
+                    if (gi + 1 < n) dst[1] -= o[b][1];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- small helpers ----------------------------------------------------------------------------
+__global__ void tr_skip_kernel(const double* __restrict__ ctrl, int mpp, int M, int* __restrict__ skip)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) skip[m] = (ctrl && ctrl[(size_t)(m / mpp) * GG_CTRL_STRIDE + GG_C_DONE] != 0.0) ? 1 : 0;
+}
+
+__global__ void tr_copy_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t per, const int* skip)
+{
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x)
+        dst[(size_t)m * per + e] = src[(size_t)m * per + e];
+}
+
+__global__ void tr_zero_kernel(double* __restrict__ dst, size_t per, const int* skip)
+{
+    const int m = blockIdx.y;
+    if (skip && skip[m]) return;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x)
+        dst[(size_t)m * per + e] = 0.0;
+}
+
+// =============================================================================================
+// host driver
+// =============================================================================================
+static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+static int dc_levels(int n)
+{
+    int L = 0;
+    while (((n + (1 << L) - 1) >> L) > DC_LEAF) ++L;
+    return L;
+}
+
+size_t gg_tridiag_ws_bytes(int M, int n)
+{
+    const size_t nn = (size_t)n * n, Mn = (size_t)M * n;
+    const int L = dc_levels(n);
+    const int npanels = (n - 1 + BT_NB - 1) / BT_NB + 1;
+    size_t b = 0;
+    b += 3 * al(sizeof(double) * M * nn);                 // Vh, Q0, U
+    b += 12 * al(sizeof(double) * Mn);                    // tau d e vbuf(2) w y lam0 lam1 z dl wnd zhat (13) -> see below
+    b += 2 * al(sizeof(double) * Mn);
+    b += al(sizeof(int) * Mn);                            // ndrow
+    b += al(sizeof(int) * (size_t)M * (1 << L));          // nodek
+    b += al(sizeof(double) * (size_t)M * (1 << L));       // noderho
+    b += al(sizeof(double) * (size_t)M * npanels * BT_NB * BT_NB);
+    b += al(sizeof(int) * (size_t)M);                     // skip
+    b += al(sizeof(double) * (size_t)M);                  // scale
+    return b;
+}
+
+// mode bits for debugging/tests: stop_after 1 = after sytrd (A holds junk; outputs d,e in D/ws), 0 = full
+int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl, int mpp, void* wsp, size_t ws_bytes,
+                         cudaStream_t s)
+{
+    if (ws_bytes < gg_tridiag_ws_bytes(M, n)) return -3;
+    const size_t nn = (size_t)n * n, Mn = (size_t)M * n;
+    const int L = dc_levels(n);
+    const int npanels = (n - 1 + BT_NB - 1) / BT_NB;
+    char* p = (char*)wsp;
+    auto take = [&](size_t bytes) { char* r = p; p += al(bytes); return r; };
+    TrWs tw;
+    DcWs dw;
+    tw.Vh = (double*)take(sizeof(double) * M * nn);
+    double* Q0 = (double*)take(sizeof(double) * M * nn);
+    dw.U = (double*)take(sizeof(double) * M * nn);
+    tw.tau = (double*)take(sizeof(double) * Mn);
+    tw.d = (double*)take(sizeof(double) * Mn);
+    tw.e = (double*)take(sizeof(double) * Mn);
+    tw.vbuf = (double*)take(sizeof(double) * 2 * Mn);
+    tw.w = (double*)take(sizeof(double) * Mn);
+    tw.y = (double*)take(sizeof(double) * Mn);
+    dw.lam[0] = (double*)take(sizeof(double) * Mn);
+    dw.lam[1] = (double*)take(sizeof(double) * Mn);
+    dw.z = (double*)take(sizeof(double) * Mn);
+    dw.dl = (double*)take(sizeof(double) * Mn);
+    dw.wnd = (double*)take(sizeof(double) * Mn);
+    dw.zhat = (double*)take(sizeof(double) * Mn);
+    dw.ndrow = (int*)take(sizeof(int) * Mn);
+    dw.nodes_max = 1 << L;
+    dw.nodek = (int*)take(sizeof(int) * (size_t)M * dw.nodes_max);
+    dw.noderho = (double*)take(sizeof(double) * (size_t)M * dw.nodes_max);
+    double* Tm = (double*)take(sizeof(double) * (size_t)M * (npanels + 1) * BT_NB * BT_NB);
+    int* skip = (int*)take(sizeof(int) * (size_t)M);
+    double* scale = (double*)take(sizeof(double) * (size_t)M);
+    static int stop_after = -1;
+    if (stop_after < 0) { const char* ev = getenv("GG_TR_STOP"); stop_after = ev ? atoi(ev) : 0; }
+
+    tr_skip_kernel<<<(M + 127) / 128, 128, 0, s>>>(ctrl, mpp, M, skip);
+    GG_CHECK_LAUNCH();
+    dim3 gz(64, M);
+    tr_zero_kernel<<<gz, 256, 0, s>>>(tw.Vh, nn, skip);
+    tr_zero_kernel<<<gz, 256, 0, s>>>(Q0, nn, skip);
+    tr_zero_kernel<<<dim3(1, M), 256, 0, s>>>(tw.tau, (size_t)n, skip);
+    GG_CHECK_LAUNCH();
+
+    // ---- stage 1 ----
+    {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(tr_symv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    }
+    if ((size_t)3 * n * sizeof(double) > 200 * 1024) return -4;
+    for (int j = 0; j < n; ++j) {
+        tr_col_kernel<<<M, 1024, 0, s>>>(A, n, j, tw, skip);
+        if (j < n - 1) {
+            const int t = n - j - 1;
+            dim3 g((t + SV_ROWS - 1) / SV_ROWS, M);
+            tr_symv_kernel<<<g, 256, sizeof(double) * 3 * t, s>>>(A, n, j, tw, skip);
+        }
+    }
+    GG_CHECK_LAUNCH();
+    if (stop_after == 1) return 0;
+
+    // ---- stage 2 ----
+    // buffers: leaves write Qt into buf[L & 1 ? ...]; arrange so that the root lands in A.
+    double* qbuf[2] = {A, Q0};           // level l merge reads qbuf[(l+1)&1], writes qbuf[l&1]; root (l=0) -> A
+    tr_zero_kernel<<<gz, 256, 0, s>>>(A, nn, skip);
+    dc_scale_kernel<<<M, 256, 0, s>>>(tw.d, tw.e, n, scale, skip);
+    if (L > 0) {
+        const int nsplit = (1 << L) - 1;
+        dc_tear_kernel<<<dim3((nsplit + 127) / 128, M), 128, 0, s>>>(tw.d, tw.e, n, L, skip);
+    }
+    dc_leaf_kernel<<<dim3(1 << L, M), 128, 0, s>>>(tw.d, tw.e, n, L, dw.lam[L & 1], qbuf[L & 1], skip);
+    GG_CHECK_LAUNCH();
+    {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(dc_secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr = true;
+        }
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        const int nodes = 1 << l;
+        const int Nmax = ((n + nodes - 1) >> l) + 1;
+        const size_t psm = sizeof(double) * 4 * Nmax + sizeof(int) * 5 * Nmax;
+        if (psm > 200 * 1024) return -4;
+        const double* Qin = qbuf[(l + 1) & 1];
+        double* Qout = qbuf[l & 1];
+        dc_prepare_kernel<<<dim3(nodes, M), 1024, psm, s>>>(tw.e, n, l, dw.lam[(l + 1) & 1], dw.lam[l & 1],
+                                                            (double*)Qin, Qout, dw, skip);
+        dc_secular_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, sizeof(double) * 2 * Nmax, s>>>(n, l, dw.lam[l & 1], dw, skip);
+        dc_zhat_kernel<<<dim3((Nmax + 255) / 256, nodes, M), 256, 0, s>>>(n, l, dw, skip);
+        dc_vectors_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, 0, s>>>(n, l, dw, skip);
+        dc_gemm_kernel<<<dim3((Nmax + DG_T - 1) / DG_T, (Nmax + DG_T - 1) / DG_T, nodes * M), 256, 0, s>>>(n, l, Qin, Qout, dw, skip);
+        GG_CHECK_LAUNCH();
+    }
+    // eigenvalues of the root are in lam[0]; eigenvectors of T (rows) in A
+    dc_unscale_kernel<<<dim3(4, M), 256, 0, s>>>(dw.lam[0], scale, n, D, skip);
+    if (stop_after == 2) return 0;
+
+    // ---- stage 3 ----
+    if (npanels > 0) {
+        bt_larft_kernel<<<dim3(npanels, M), 256, 0, s>>>(tw.Vh, tw.tau, n, Tm, npanels, skip);
+        bt_apply_kernel<<<dim3((n + BT_R - 1) / BT_R, M), 256, 0, s>>>(A, tw.Vh, Tm, n, npanels, skip);
+    }
+    GG_CHECK_LAUNCH();
+    return 0;
+}

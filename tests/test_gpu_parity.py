@@ -38,7 +38,20 @@ def _sym(rng, p, scale=1.0):
 # --------------------------------------------------------------------------------------------
 # eigensolver + spectral reconstruction
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("p", [1, 2, 3, 10, 37, 100, 160, 161, 200, 333, 512])
+@pytest.mark.parametrize("p,nb2", [(161, 32), (200, 64), (333, 32), (512, 128)])
+def test_eigh_block_jacobi_path(p, nb2):
+    from gglasso_b200._engine import eigh
+    rng = np.random.default_rng(p)
+    A = np.stack([_sym(rng, p) for _ in range(2)])
+    D, Q = eigh(A, nb2=nb2)
+    Dref = np.linalg.eigvalsh(A)
+    assert np.abs(D - Dref).max() < 1e-11 * p ** 0.5 * (np.abs(Dref).max() + 1)
+    for m in range(2):
+        assert np.abs(Q[m].T @ Q[m] - np.eye(p)).max() < 1e-12
+        assert np.abs(A[m] @ Q[m] - Q[m] * D[m]).max() < 2e-12 * p ** 0.5 * (np.abs(Dref).max() + 1)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 10, 37, 100, 160, 161, 200, 333, 512, 777, 1000])
 def test_eigh_matches_lapack(p):
     from gglasso_b200._engine import eigh
     rng = np.random.default_rng(p)
