@@ -23,7 +23,17 @@ size_t gg_eigh_ws_bytes(int, int);
 int gg_eigh_impl(double*, double*, int, int, const double*, int, void*, size_t, int, int, double, int, double, int*,
                  cudaStream_t);
 
+int gg_eigh_tridiag_impl(double*, double*, int, int, const double*, int, void*, size_t, cudaStream_t, int);
+size_t gg_tridiag_ws_bytes(int, int);
+
 extern "C" {
+
+int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_bytes, int which, void* stream)
+{
+    if (M <= 0 || p <= 160 || which < 0 || which > 2) return -1;
+    if (ws_bytes < gg_tridiag_ws_bytes(M, p)) return -3;
+    return gg_eigh_tridiag_impl(A, D, M, p, nullptr, 1, ws, ws_bytes, (cudaStream_t)stream, which == 0 ? 3 : which);
+}
 
 int gg_version(void) { return 100; }
 

@@ -374,7 +374,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 size_t gg_tridiag_ws_bytes(int M, int n);
 int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl, int mpp, void* wsp, size_t ws_bytes,
-                         cudaStream_t s);
+                         cudaStream_t s, int which);
 
 static size_t gg_jacobi_ws_bytes(int M, int p)
 {
@@ -457,7 +457,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
 
     // ---- large p: tridiagonalisation + divide & conquer (default), or block Jacobi on request ----
     if (block_nb2 != 32 && block_nb2 != 64 && block_nb2 != 128) {
-        const int rc = gg_eigh_tridiag_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, s);
+        const int rc = gg_eigh_tridiag_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, s, 0);
         if (info) info[0] = -1;
         return rc;
     }

@@ -112,9 +112,8 @@ tr_col_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restri
 
 // Streams the trailing block rows i in (j, n): a_ik -= vp_i w_k + w_i vp_k (pending step j-1), then
 // y_i = sum_k a_ik v_k.  Full symmetric storage: every row is complete, no atomics.
-#define SV_ROWS 32
 __global__ void __launch_bounds__(256)
-tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip)
+tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip, int SV_ROWS)
 {
     extern __shared__ double sv[];           // vp[t], w[t], v[t]
     const int m = blockIdx.y;
@@ -811,7 +810,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
 
 // mode bits for debugging/tests: stop_after 1 = after sytrd (A holds junk; outputs d,e in D/ws), 0 = full
 int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl, int mpp, void* wsp, size_t ws_bytes,
-                         cudaStream_t s)
+                         cudaStream_t s, int which)
 {
     if (ws_bytes < gg_tridiag_ws_bytes(M, n)) return -3;
     const size_t nn = (size_t)n * n, Mn = (size_t)M * n;
@@ -861,15 +860,18 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     }
     if ((size_t)3 * n * sizeof(double) > 200 * 1024) return -4;
     for (int j = 0; j < n; ++j) {
-        tr_col_kernel<<<M, 1024, 0, s>>>(A, n, j, tw, skip);
-        if (j < n - 1) {
+        if (which != 2) tr_col_kernel<<<M, 1024, 0, s>>>(A, n, j, tw, skip);
+        if (j < n - 1 && which != 1) {
             const int t = n - j - 1;
-            dim3 g((t + SV_ROWS - 1) / SV_ROWS, M);
-            tr_symv_kernel<<<g, 256, sizeof(double) * 3 * t, s>>>(A, n, j, tw, skip);
+            // rows per CTA: fill ~2 CTAs per SM across the batch, 8..32 rows (one to four per warp)
+            int rows = (int)(((long long)t * M) / 296);
+            rows = rows < 8 ? 8 : (rows > 32 ? 32 : (rows + 7) / 8 * 8);
+            dim3 g((t + rows - 1) / rows, M);
+            tr_symv_kernel<<<g, 256, sizeof(double) * 3 * t, s>>>(A, n, j, tw, skip, rows);
         }
     }
     GG_CHECK_LAUNCH();
-    if (stop_after == 1) return 0;
+    if (stop_after == 1 || which != 0) return 0;
 
     // ---- stage 2 ----
     // buffers: leaves write Qt into buf[L & 1 ? ...]; arrange so that the root lands in A.

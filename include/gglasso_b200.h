@@ -51,6 +51,11 @@ size_t gg_eigh_workspace_bytes(int M, int p);
 int gg_eigh(double* A, double* D, int M, int p, const double* ctrl, int mpp, void* ws, size_t ws_bytes,
             int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, void* stream);
 
+/* Stage 1 of the large-p eigensolver only (Householder tridiagonalisation of the batch), for profiling:
+ * which = 0 full sytrd, 1 only the per-column kernels, 2 only the trailing-matrix (symv + rank-2 update)
+ * kernels.  Results of which != 0 are meaningless; A is destroyed.  p must exceed 160. */
+int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_bytes, int which, void* stream);
+
 /* Out = V diag(f(D)) V^T with V^T = Vt from gg_eigh (FP64 tensor cores, exactly symmetric result).
  * mode 0: f = phi+(d, beta) = (sqrt(d^2+4 beta)+d)/2   src/gglasso/solver/ggl_helper.py:272-303
  * mode 1: f = max(d-beta, 0)                            src/gglasso/solver/ggl_helper.py:29-36
