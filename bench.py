@@ -15,9 +15,11 @@ A "step" is one ADMM iteration over the whole (K,p,p) stack.
   cpu_baseline : the oracle port (numpy/LAPACK + C prox; same algorithm as the reference) timed on
           the host cores for a bounded number of iterations of the same workload
 
-N > 1 (torchrun, one rank per GPU): the K instances' eigendecompositions are independent, so each
-rank runs an independent replica group of the workload (weak scaling, no data-path collective);
-`value` is the aggregate iterations/sec.
+N > 1 (torchrun, one rank per GPU): ONE fused-MGL problem with K = 20*N instances, 20 per rank (weak
+scaling).  Everything per instance stays local; the cross-instance TV prox needs all K values of an entry,
+so V = Omega + X is re-tiled instance-layout -> row-band layout with an NCCL all-to-all, the prox runs on the
+band and Theta travels back with a second all-to-all; 5 residual sums are all-reduced.  `value` counts units of
+(K=20, p=1000) stacks processed per second over all ranks = N * iterations/sec.
 --impl reference : rank 0 times the CPU oracle port on the same config.
 """
 import argparse
@@ -145,7 +147,6 @@ def main():
     S = make_input(cfg)
     K, p = cfg["K"], cfg["p"]
     Om0 = np.repeat(np.eye(p)[None], K, 0)
-    Z = np.zeros_like(S)
     steps, warm = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -170,9 +171,16 @@ def main():
         return orig_step(self)
 
     eng.AdmmState.omega_step = stepped
+    from gglasso_b200.parallel import ADMM_MGL_dist, run_admm_mgl_dist
     with ClockSampler(local) as clk:
-        st, res = run_admm("mgl", S, Om0, Om0, Z, lambda1=cfg["lambda1"], lambda2=cfg["lambda2"], reg=cfg["reg"],
-                           tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
+        if world == 1:
+            st, res = run_admm("mgl", S, Om0, None, None, lambda1=cfg["lambda1"], lambda2=cfg["lambda2"],
+                               reg=cfg["reg"], tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
+        else:
+            # one MGL problem with K = 20*N instances, 20 per rank: per-instance work stays local, the
+            # cross-instance prox goes through two all-to-all re-tiles per iteration (weak scaling)
+            st, _ = run_admm_mgl_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K * world,
+                                      tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         barrier()
@@ -192,15 +200,20 @@ def main():
     barrier()
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
-        sol, info = ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=0.0, rtol=0.0, max_iter=steps)
+        if world == 1:
+            sol, info = ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=0.0, rtol=0.0, max_iter=steps)
+        else:
+            sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K * world,
+                                      tol=0.0, rtol=0.0, max_iter=steps, check_every=10 ** 9)
+            sol.pop("L")
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = world * steps / float(t.item())
-    h2d = (S.nbytes + Om0.nbytes * 2 + Z.nbytes) / steps
-    d2h = sum(v.nbytes for v in sol.values()) / steps
+    h2d = world * (S.nbytes + Om0.nbytes) / steps
+    d2h = world * sum(v.nbytes for k, v in sol.items() if not (k == "L")) / steps
 
     if rank == 0:
         cpu = None
@@ -214,7 +227,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "cfg3: ADMM_MGL FGL K=20 p=1000 N=2000 lambda1=0.05 lambda2=0.01", **CFG,
                            "l2": "inputs larger than L2 (each (K,p,p) FP64 array is 160 MB; >10 arrays per step)",
-                           "replicas_per_gpu": 1, "eigh": "sytrd + divide&conquer + ormtr (hand-written)"},
+                           "K_total": K * world, "partition": "K-sharded (20 instances per GPU); cross-instance prox via 2 all-to-all re-tiles per iteration" if world > 1 else "single GPU",
+                           "eigh": "sytrd + divide&conquer + ormtr (hand-written)"},
                 "e2e": {"value": e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
@@ -234,7 +248,8 @@ def launches_per_iter(p, K, sweeps):
 
 def kernel_roofline(st, sweeps, ms_per_step):
     """Dominant kernel of the step: tr_symv_kernel (trailing-matrix pass of the Householder
-    tridiagonalisation: applies the pending rank-2 update and accumulates A*v in one sweep; HBM/L2 bound).
+    tridiagonalisation: applies the pending rank-2 update to the upper triangle and accumulates the full
+    symmetric A*v from that one half-matrix sweep; HBM/L2 bound).
     Timed live with CUDA events on the launch stream through gg_sytrd_profile(which=2), which issues
     exactly the (p-1) symv launches of one eigendecomposition of the batch."""
     import ctypes
@@ -269,8 +284,9 @@ def kernel_roofline(st, sweeps, ms_per_step):
                 best = min(best, a.elapsed_time(b))
         times[which] = best
     n_launch = p - 1
-    # algorithmic bytes of launch j: read + write of the (p-j-1)^2 trailing block of each of the M matrices
-    total_bytes = sum(16.0 * M * (p - j - 1) ** 2 for j in range(p - 1))
+    # algorithmic bytes of launch j: read + write of the UPPER TRIANGLE of the t x t trailing block (t = p-j-1)
+    # of each of the M matrices: 16 * t(t+1)/2 bytes
+    total_bytes = sum(16.0 * M * (p - j - 1) * (p - j) / 2 for j in range(p - 1))
     achieved = total_bytes / (times[2] * 1e-3) / 1e9            # GB/s over all symv launches of one eigh
     return {"bound": "hbm", "kernel": "tr_symv_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
             "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,

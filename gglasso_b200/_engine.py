@@ -46,6 +46,39 @@ def to_dev(a, dev):
     return torch.from_numpy(a).to(dev, non_blocking=False)
 
 
+_STAGE = {}
+
+
+def to_host(t, chunk_bytes=32 << 20):
+    """device tensor -> fresh numpy array through two pinned staging buffers (chunked, copy of chunk i+1
+    overlaps the host-side memcpy of chunk i).  Pageable cudaMemcpy reaches only ~2 GB/s on the GPU boxes."""
+    t = t.contiguous()
+    n = t.numel()
+    out = np.empty(tuple(t.shape), dtype=np.float64)
+    if n * 8 <= (1 << 20):
+        out[...] = t.cpu().numpy()
+        return out
+    ce = chunk_bytes // 8
+    if "bufs" not in _STAGE:
+        _STAGE["bufs"] = [torch.empty(ce, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        _STAGE["evs"] = [torch.cuda.Event(), torch.cuda.Event()]
+    bufs, evs = _STAGE["bufs"], _STAGE["evs"]
+    src = t.view(-1)
+    dst = torch.from_numpy(out).view(-1)
+    nchunks = (n + ce - 1) // ce
+    for i in range(nchunks + 1):
+        if i < nchunks:
+            lo, hi = i * ce, min(n, (i + 1) * ce)
+            bufs[i & 1][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+            evs[i & 1].record()
+        if i >= 1:
+            j = i - 1
+            lo, hi = j * ce, min(n, (j + 1) * ce)
+            evs[j & 1].synchronize()
+            dst[lo:hi].copy_(bufs[j & 1][:hi - lo])
+    return out
+
+
 class Eigh:
     """workspace + call wrapper for gg_eigh / gg_recon on (M,p,p) stacks."""
 
@@ -110,8 +143,9 @@ class AdmmState:
         self.Omega_new = torch.empty_like(self.Omega)
         self._bufA, self._bufB = self.Omega, self.Omega_new
         self.nswap = 0
-        self.Theta = to_dev(Theta_0, dev)
-        self.X = to_dev(X_0, dev)
+        # defaults of the reference (admm_solver.py:143-146) are formed on the device: no extra uploads
+        self.Theta = self.Omega.clone() if Theta_0 is None else to_dev(Theta_0, dev)
+        self.X = torch.zeros_like(self.S) if X_0 is None else to_dev(X_0, dev)
         self.L = torch.zeros_like(self.S) if latent else None
         self.W = torch.empty_like(self.S)
         self.eig = Eigh(self.M, self.p, dev)
@@ -176,7 +210,8 @@ class AdmmState:
 
 def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None, lam_mat=None, rho=1.0,
              max_iter=1000, tol=1e-7, rtol=1e-4, stopping_criterion="boyd", update_rho=True, verbose=False,
-             measure=False, latent=False, mu=None, nk=None, header=None, check_every=None, trace=None):
+             measure=False, latent=False, mu=None, nk=None, header=None, check_every=None, trace=None,
+             check_symmetric=False):
     """Run the device ADMM loop.  ``kind``: 'mgl' (one problem of K matrices) or 'sgl' (M problems).
 
     Returns (state, info) where info carries iteration counts, status and histories (numpy).
@@ -184,11 +219,15 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     S3 = S if S.ndim == 3 else S[None]
     M, p, _ = S3.shape
     mpp = M if kind == "mgl" else 1
-    st = AdmmState(S3, Omega_0.reshape(S3.shape), Theta_0.reshape(S3.shape), X_0.reshape(S3.shape), mpp, rho,
-                   max_iter, latent, nk=nk, mu=mu, lam_mat=lam_mat)
+    st = AdmmState(S3, Omega_0.reshape(S3.shape), None if Theta_0 is None else Theta_0.reshape(S3.shape),
+                   None if X_0 is None else X_0.reshape(S3.shape), mpp, rho, max_iter, latent, nk=nk, mu=mu,
+                   lam_mat=lam_mat)
     lib, stream = st.lib, st.stream
     nprob = st.nprob
     regi = {"GGL": 0, "FGL": 1}.get(reg, -1)
+    if check_symmetric:
+        for A in (st.S, st.Omega, st.Theta, st.X):
+            assert st.asym_max(A) <= 1e-5, "input X is not symmetric"
 
     if kind == "mgl":
         nt = lib.gg_mgl_ntile(p)

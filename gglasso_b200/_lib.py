@@ -29,6 +29,8 @@ SIGNATURES = {
     "gg_prox_sgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _i, _vp, _vp]),
     "gg_mgl_ntile": (_i, [_i]),
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
+    "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "gg_prox_band": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, _i, _i, _i, _vp]),
     "gg_dual_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gg_stop_update": (_i, [_vp, _i, _vp, _vp, _i, _vp, _d, _d, _i, _i, _vp]),
     "gg_scale_pending": (_i, [_vp, _vp, _i, _i, _i, _vp]),

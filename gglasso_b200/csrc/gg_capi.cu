@@ -24,6 +24,8 @@ int gg_eigh_impl(double*, double*, int, int, const double*, int, void*, size_t, 
                  cudaStream_t);
 
 int gg_eigh_tridiag_impl(double*, double*, int, int, const double*, int, void*, size_t, cudaStream_t, int);
+int gg_launch_add3(const double*, const double*, const double*, double*, size_t, cudaStream_t);
+int gg_launch_prox_band(const double*, double*, const double*, double, double, int, int, int, int, int, cudaStream_t);
 size_t gg_tridiag_ws_bytes(int, int);
 
 extern "C" {
@@ -111,6 +113,19 @@ int gg_asym_max(const double* A, int M, int p, double* out, void* stream)
 {
     if (M <= 0 || p <= 0) return -1;
     return gg_launch_asym_max(A, M, p, out, (cudaStream_t)stream);
+}
+
+int gg_add3(const double* Omega, const double* L, const double* X, double* V, size_t total, void* stream)
+{
+    if (total == 0) return 0;
+    return gg_launch_add3(Omega, L, X, V, total, (cudaStream_t)stream);
+}
+
+int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lambda1, double lambda2, int reg, int K,
+                 int nb, int p, int row0, void* stream)
+{
+    if (K <= 0 || nb < 0 || p <= 0 || reg < 0 || reg > 1) return -1;
+    return gg_launch_prox_band(V, Theta, ctrl, lambda1, lambda2, reg, K, nb, p, row0, (cudaStream_t)stream);
 }
 
 void gg_host_tv1d(double* v, int n, int stride, double lam) { gg_tv1d_inplace(v, n, stride, lam); }

@@ -124,9 +124,10 @@ dual_update_kernel(double* __restrict__ X, const double* __restrict__ Omega, con
     const size_t stride = (size_t)gridDim.x * EW_THREADS;
     double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += stride) {
-        const double om = Omega[base + e], th = Theta[base + e], l = L[base + e], x = X[base + e];
-        const double res = (om - th) + l;                         // Omega - Theta + L
-        const double xn = sgl_order ? (((x + om) - th) + l) : (x + res);
+        const double om = Omega[base + e], th = Theta[base + e], x = X[base + e];
+        const double l = L ? L[base + e] : 0.0;
+        const double res = L ? ((om - th) + l) : (om - th);       // Omega - Theta + L
+        const double xn = sgl_order ? (L ? (((x + om) - th) + l) : ((x + om) - th)) : (x + res);
         X[base + e] = xn;
         const double tl = th - l, d2 = om - Omega_prev[base + e];
         acc[0] += om * om; acc[1] += tl * tl; acc[2] += xn * xn; acc[3] += res * res; acc[4] += d2 * d2;
@@ -358,6 +359,60 @@ asym_max_kernel(const double* __restrict__ A, int p, double* __restrict__ out)
     if (threadIdx.x == 0) out[(size_t)m * gridDim.x + blockIdx.x] = mx;
 }
 
+// ------------------------------------------------------------------------------------------
+// K-sharded MGL (one process per GPU): V = (Omega + L) + X is exchanged from instance layout to row-band
+// layout, the cross-instance prox runs on the band, Theta travels back.
+__global__ void __launch_bounds__(EW_THREADS)
+add3_kernel(const double* __restrict__ Omega, const double* __restrict__ L, const double* __restrict__ X,
+            double* __restrict__ V, size_t total)
+{
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * EW_THREADS) {
+        double v = Omega[e];
+        if (L) v = v + L[e];
+        V[e] = v + X[e];
+    }
+}
+
+// V, Theta: (K, nb, p) slabs holding global rows row0..row0+nb-1 of every instance.  One thread per entry;
+// the K-vector lives in shared memory ([k][tid]: conflict free).  Every entry is computed from its own
+// inputs, so with symmetric inputs the assembled Theta is symmetric and identical to prox_mgl_kernel's.
+template <int REG>
+__global__ void __launch_bounds__(256)
+prox_band_kernel(const double* __restrict__ V, double* __restrict__ Theta, const double* __restrict__ ctrl,
+                 double lambda1, double lambda2, int K, int nb, int p, int row0)
+{
+    extern __shared__ double ysm[];              // K * 256
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const double inv_rho = 1.0 / ctrl[GG_C_RHO];
+    const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
+    const size_t slab = (size_t)nb * p;
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= slab) return;
+    const int r = (int)(e / p), c = (int)(e - (size_t)r * p);
+    double* y = ysm + threadIdx.x;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) y[k * 256] = V[k * slab + e];
+    if (row0 + r != c) {
+        if (REG == 0) {
+            double ss = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double u = gg_soft(y[k * 256], l1);
+                y[k * 256] = u;
+                ss += u * u;
+            }
+            const double nrm = sqrt(ss);
+            const double a = nrm > l2 ? nrm : l2;
+            const double f = a - l2;
+            for (int k = 0; k < K; ++k) y[k * 256] = (y[k * 256] * f) / a;
+        } else {
+            gg_tv1d_inplace(y, K, 256, l2);
+            for (int k = 0; k < K; ++k) y[k * 256] = gg_soft(y[k * 256], l1);
+        }
+    }
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) Theta[k * slab + e] = y[k * 256];
+}
+
 // ==========================================================================================
 // host launchers (C++ linkage; the extern "C" ABI lives in gg_capi.cu)
 // ==========================================================================================
@@ -472,6 +527,34 @@ int gg_launch_asym_max(const double* A, int M, int p, double* out, cudaStream_t 
 {
     dim3 grid(gg_sgl_nparts(p, M), M);
     asym_max_kernel<<<grid, EW_THREADS, 0, st>>>(A, p, out);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_add3(const double* Omega, const double* L, const double* X, double* V, size_t total, cudaStream_t st)
+{
+    size_t blocks = (total + EW_THREADS - 1) / EW_THREADS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    add3_kernel<<<(unsigned)blocks, EW_THREADS, 0, st>>>(Omega, L, X, V, total);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_prox_band(const double* V, double* Theta, const double* ctrl, double l1, double l2, int reg, int K,
+                        int nb, int p, int row0, cudaStream_t st)
+{
+    const size_t smem = (size_t)K * 256 * sizeof(double);
+    if (smem > 200 * 1024) return -2;
+    const size_t slab = (size_t)nb * p;
+    const unsigned grid = (unsigned)((slab + 255) / 256);
+    if (grid == 0) return 0;
+    if (reg == 0) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prox_band_kernel<0><<<grid, 256, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prox_band_kernel<1><<<grid, 256, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
+    }
     GG_CHECK_LAUNCH();
     return 0;
 }

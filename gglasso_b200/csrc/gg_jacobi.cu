@@ -457,7 +457,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
 
     // ---- large p: tridiagonalisation + divide & conquer (default), or block Jacobi on request ----
     if (block_nb2 != 32 && block_nb2 != 64 && block_nb2 != 128) {
-        const int rc = gg_eigh_tridiag_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, s, 0);
+        const int rc = gg_eigh_tridiag_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, s, vectors ? 0 : 4);
         if (info) info[0] = -1;
         return rc;
     }

@@ -70,6 +70,11 @@ tr_col_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restri
         __syncthreads();
         wj = w[j];                                   // v^{(j-1)}[j] = 1
     }
+    // y is accumulated with atomics by the next tr_symv_kernel: clear it now that it has been consumed
+    {
+        double* yz = ws.y + (size_t)m * n;
+        for (int i = tid; i < n; i += nt) yz[i] = 0.0;
+    }
     // row j (== column j) of the trailing block, with the pending update of step j-1 applied
     // a_i = A[j][i] - v_i w_j - w_i v_j ,  i in j..n-1
     double* rowj = Am + (size_t)j * n;
@@ -110,50 +115,82 @@ tr_col_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restri
     }
 }
 
-// Streams the trailing block rows i in (j, n): a_ik -= vp_i w_k + w_i vp_k (pending step j-1), then
-// y_i = sum_k a_ik v_k.  Full symmetric storage: every row is complete, no atomics.
+// Streams the UPPER triangle of the trailing block, one CTA per 64x64 tile (I <= J): applies the pending
+// rank-2 update of step j-1 (a_rc -= vp_r w_c + w_r vp_c), writes the tile back, and accumulates the full
+// symmetric y = A v from that single pass: y_I += T v_J (row sums) and, mirrored, y_J += T^T v_I (column sums;
+// strictly upper part on diagonal tiles).  Half the traffic of a full-matrix pass; 128 FP64 atomics per tile.
+#define SV_T 64
 __global__ void __launch_bounds__(256)
-tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip, int SV_ROWS)
+tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip, int nt)
 {
-    extern __shared__ double sv[];           // vp[t], w[t], v[t]
+    __shared__ double tile[SV_T][SV_T + 1];
+    __shared__ double s_vpI[SV_T], s_wI[SV_T], s_vI[SV_T], s_vpJ[SV_T], s_wJ[SV_T], s_vJ[SV_T];
     const int m = blockIdx.y;
     if (skip && skip[m]) return;
     const int t = n - j - 1;
     const int base = j + 1;
-    double* s_vp = sv;
-    double* s_w = sv + t;
-    double* s_v = sv + 2 * t;
-    const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;
-    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n;
-    const double* w = ws.w + (size_t)m * n;
+    int idx = blockIdx.x, I = 0;
+    while (idx >= nt - I) { idx -= nt - I; ++I; }
+    const int J = I + idx;
+    const int r0 = I * SV_T, c0 = J * SV_T;
+    const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n + base;
+    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
+    const double* w = ws.w + (size_t)m * n + base;
     const bool pend = (j >= 1);
-    for (int k = threadIdx.x; k < t; k += 256) {
-        s_vp[k] = pend ? vprev[base + k] : 0.0;
-        s_w[k] = pend ? w[base + k] : 0.0;
-        s_v[k] = vcur[base + k];
+    const int tid = threadIdx.x;
+    if (tid < SV_T) {
+        const int r = r0 + tid;
+        const bool ok = r < t;
+        s_vpI[tid] = (ok && pend) ? vprev[r] : 0.0;
+        s_wI[tid] = (ok && pend) ? w[r] : 0.0;
+        s_vI[tid] = ok ? vcur[r] : 0.0;
+    } else if (tid < 2 * SV_T) {
+        const int c = c0 + tid - SV_T;
+        const bool ok = c < t;
+        s_vpJ[tid - SV_T] = (ok && pend) ? vprev[c] : 0.0;
+        s_wJ[tid - SV_T] = (ok && pend) ? w[c] : 0.0;
+        s_vJ[tid - SV_T] = ok ? vcur[c] : 0.0;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double* Am = A + (size_t)m * n * n;
-    double* y = ws.y + (size_t)m * n;
-    for (int r = wid; r < SV_ROWS; r += 8) {
-        const int il = blockIdx.x * SV_ROWS + r;      // local row
-        if (il >= t) break;
-        double* row = Am + (size_t)(base + il) * n + base;
-        const double vpi = s_vp[il], wi = s_w[il];
-        double acc = 0.0;
-        if (pend) {
-            for (int k = lane; k < t; k += 32) {
-                double a = row[k];
-                a = a - vpi * s_w[k] - wi * s_vp[k];
-                row[k] = a;
-                acc = fma(a, s_v[k], acc);
+    double* Am = A + (size_t)m * n * n + (size_t)base * n + base;
+    const int cl = tid & 63, rq = tid >> 6;          // column in tile, row quarter
+    const int c = c0 + cl;
+    double a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int r = r0 + rq + 4 * q;
+        a[q] = (r < t && c < t && c >= r) ? Am[(size_t)r * n + c] : 0.0;
+    }
+    if (pend) {
+        const double wc = s_wJ[cl], vpc = s_vpJ[cl];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int rl = rq + 4 * q, r = r0 + rl;
+            if (r < t && c < t && c >= r) {
+                a[q] = a[q] - s_vpI[rl] * wc - s_wI[rl] * vpc;
+                Am[(size_t)r * n + c] = a[q];
             }
-        } else {
-            for (int k = lane; k < t; k += 32) acc = fma(row[k], s_v[k], acc);
         }
-        acc = gg_warp_sum(acc);
-        if (lane == 0) y[base + il] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) tile[rq + 4 * q][cl] = a[q];
+    __syncthreads();
+    double* y = ws.y + (size_t)m * n + base;
+    if (tid < SV_T) {                                  // row sums -> y_I (includes the diagonal)
+        double s = 0.0;
+#pragma unroll 8
+        for (int cc = 0; cc < SV_T; ++cc) s = fma(tile[tid][cc], s_vJ[cc], s);
+        if (r0 + tid < t) atomicAdd(y + r0 + tid, s);
+    } else if (tid < 2 * SV_T) {                       // column sums -> y_J (strictly upper part only)
+        const int cc = tid - SV_T;
+        double s = 0.0;
+        if (I == J) {
+            for (int rr = 0; rr < cc; ++rr) s = fma(tile[rr][cc], s_vI[rr], s);
+        } else {
+#pragma unroll 8
+            for (int rr = 0; rr < SV_T; ++rr) s = fma(tile[rr][cc], s_vI[rr], s);
+        }
+        if (c0 + cc < t) atomicAdd(y + c0 + cc, s);
     }
 }
 
@@ -854,24 +891,17 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     GG_CHECK_LAUNCH();
 
     // ---- stage 1 ----
-    {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(tr_symv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-    }
-    if ((size_t)3 * n * sizeof(double) > 200 * 1024) return -4;
     for (int j = 0; j < n; ++j) {
         if (which != 2) tr_col_kernel<<<M, 1024, 0, s>>>(A, n, j, tw, skip);
         if (j < n - 1 && which != 1) {
             const int t = n - j - 1;
-            // rows per CTA: fill ~2 CTAs per SM across the batch, 8..32 rows (one to four per warp)
-            int rows = (int)(((long long)t * M) / 296);
-            rows = rows < 8 ? 8 : (rows > 32 ? 32 : (rows + 7) / 8 * 8);
-            dim3 g((t + rows - 1) / rows, M);
-            tr_symv_kernel<<<g, 256, sizeof(double) * 3 * t, s>>>(A, n, j, tw, skip, rows);
+            const int nt = (t + SV_T - 1) / SV_T;
+            dim3 g(nt * (nt + 1) / 2, M);
+            tr_symv_kernel<<<g, 256, 0, s>>>(A, n, j, tw, skip, nt);
         }
     }
     GG_CHECK_LAUNCH();
-    if (stop_after == 1 || which != 0) return 0;
+    if (stop_after == 1 || (which != 0 && which != 4)) return 0;
 
     // ---- stage 2 ----
     // buffers: leaves write Qt into buf[L & 1 ? ...]; arrange so that the root lands in A.
@@ -912,7 +942,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     if (stop_after == 2) return 0;
 
     // ---- stage 3 ----
-    if (npanels > 0) {
+    if (npanels > 0 && which != 4) {
         bt_larft_kernel<<<dim3(npanels, M), 256, 0, s>>>(tw.Vh, tw.tau, n, Tm, npanels, skip);
         bt_apply_kernel<<<dim3((n + BT_R - 1) / BT_R, M), 256, 0, s>>>(A, tw.Vh, Tm, n, npanels, skip);
     }

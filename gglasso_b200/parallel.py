@@ -1,0 +1,251 @@
+"""Multi-GPU partitioning of the ADMM hot path (one process per GPU, torch.distributed).
+
+Three natural seams:
+
+* ``ADMM_MGL_dist``   one large-K MGL solve: the K instances are sharded across ranks for everything
+                      that is per instance (W build, eigendecomposition, phi+ reconstruction, L step, dual
+                      update); the cross-instance prox (``prox_p``, src/gglasso/solver/ggl_helper.py:190-207)
+                      needs all K values of an entry, so ``V = Omega + L + X`` is re-tiled from instance layout
+                      to row-band layout with one all-to-all, the prox runs on the band, and Theta travels
+                      back with a second all-to-all.  The five residual sums are all-reduced (5 doubles) and
+                      every rank takes the same rho / stopping decision.
+* ``grid_search_dist`` lambda1 x lambda2 model-selection grid (src/gglasso/helper/model_selection.py:55-298):
+                      lambda1 columns are dealt to ranks; inside a column the reference's warm-start chain
+                      (``Omega_0 = previous Omega``, :224) is kept; no collective during the solves, one
+                      gather of the per-grid-point scores at the end.
+* ``assign_blocks``   LPT assignment of block_SGL's connected components (cost ~ size^3) to ranks.
+
+The re-tile helpers work on CPU tensors over gloo as well, which is how the host logic is tested without GPUs.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition(n, parts):
+    """balanced contiguous partition of range(n) into ``parts`` pieces -> list of (lo, hi)."""
+    base, rem = divmod(n, parts)
+    out, lo = [], 0
+    for r in range(parts):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class KShard:
+    """layout bookkeeping for a K-sharded (K_total, p, p) stack."""
+
+    def __init__(self, K_total, p, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.K_total, self.p = K_total, p
+        self.kparts = partition(K_total, self.world)
+        self.rparts = partition(p, self.world)
+        self.k_lo, self.k_hi = self.kparts[self.rank]
+        self.r_lo, self.r_hi = self.rparts[self.rank]
+        self.K_loc = self.k_hi - self.k_lo
+        self.nb = self.r_hi - self.r_lo
+
+    # (K_loc, p, p) -> (K_total, nb, p): every rank ends up with its row band of ALL instances
+    def to_band(self, x):
+        p = self.p
+        if self.world == 1:
+            return x[:, self.r_lo:self.r_hi, :].contiguous()
+        send = torch.cat([x[:, lo:hi, :].reshape(-1) for lo, hi in self.rparts])
+        in_split = [self.K_loc * (hi - lo) * p for lo, hi in self.rparts]
+        out_split = [(khi - klo) * self.nb * p for klo, khi in self.kparts]
+        recv = torch.empty(sum(out_split), dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(recv, send, out_split, in_split, group=self.group)
+        return recv.view(self.K_total, self.nb, p)
+
+    # (K_total, nb, p) -> (K_loc, p, p)
+    def from_band(self, y):
+        p = self.p
+        if self.world == 1:
+            out = torch.empty((self.K_loc, p, p), dtype=y.dtype, device=y.device)
+            out[:, self.r_lo:self.r_hi, :] = y
+            return out
+        y = y.contiguous()
+        in_split = [(khi - klo) * self.nb * p for klo, khi in self.kparts]
+        out_split = [self.K_loc * (hi - lo) * p for lo, hi in self.rparts]
+        recv = torch.empty(sum(out_split), dtype=y.dtype, device=y.device)
+        dist.all_to_all_single(recv, y.view(-1), out_split, in_split, group=self.group)
+        out = torch.empty((self.K_loc, p, p), dtype=y.dtype, device=y.device)
+        off = 0
+        for (lo, hi), n in zip(self.rparts, out_split):
+            out[:, lo:hi, :] = recv[off:off + n].view(self.K_loc, hi - lo, p)
+            off += n
+        return out
+
+    def allreduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def ADMM_MGL_dist(S_local, lambda1, lambda2, reg, Omega_0_local, **kw):
+    """K-sharded ADMM_MGL ('boyd' criterion).  Each rank passes ITS contiguous block of instances
+    (rank r owns instances partition(K_total, world)[r]) and gets the matching block of the solution back.
+
+    Keyword arguments: K_total, Theta_0_local, X_0_local, n_samples, tol, rtol, update_rho, rho, max_iter, verbose,
+    latent, mu1_local, group, check_every.
+    Returns (sol_local, info); info = {'status', 'iterations', 'residual'} identical on every rank.
+    """
+    from ._engine import to_host
+    st, info = run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, **kw)
+    latent = kw.get("latent", False)
+    Omega = st.final_omega([info["iterations"]])
+    sol = {"Omega": to_host(Omega), "Theta": to_host(st.Theta), "X": to_host(st.X),
+           "L": to_host(st.L) if latent else np.zeros_like(S_local)}
+    return sol, info
+
+
+def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=None, Theta_0_local=None,
+                      X_0_local=None, n_samples=None, tol=1e-5, rtol=1e-4, update_rho=True, rho=1., max_iter=1000,
+                      verbose=False, latent=False, mu1_local=None, group=None, check_every=1):
+    """device loop of ADMM_MGL_dist; returns (AdmmState, info) without copying the solution to the host."""
+    from . import _lib
+    from ._engine import AdmmState, _p
+    from ._lib import C_DONE, C_ITER, NPART
+    assert reg in ['GGL', 'FGL'] and min(lambda1, lambda2) > 0 and rho > 0
+    K_loc, p, _ = S_local.shape
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if K_total is None:
+        t = torch.tensor([K_loc], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, group=group)
+        K_total = int(t.item())
+    sh = KShard(K_total, p, group)
+    assert sh.K_loc == K_loc, "each rank must hold partition(K_total, world)[rank] instances"
+    nk = None if n_samples is None else float(n_samples) * np.ones(K_loc)
+    mu = None
+    if latent:
+        mu = (mu1_local * np.ones(K_loc)) if np.isscalar(mu1_local) else np.asarray(mu1_local, dtype=np.float64)
+    st = AdmmState(S_local, Omega_0_local, Theta_0_local, X_0_local, K_loc, rho, max_iter, latent, nk=nk, mu=mu)
+    st.pdim.fill_(K_total * ((p ** 2 + p) / 2))
+    lib, stream = st.lib, st.stream
+    regi = 0 if reg == "GGL" else 1
+    V = torch.empty_like(st.S)
+    nparts = lib.gg_sgl_nparts(p, K_loc) * K_loc
+    partials = torch.zeros((nparts, NPART), dtype=torch.float64, device=st.dev)
+    tot = torch.zeros((1, NPART), dtype=torch.float64, device=st.dev)
+    total = K_loc * p * p
+
+    for it in range(max_iter):
+        st.omega_step()
+        _lib.check(lib.gg_add3(_p(st.Omega_new), _p(st.L), _p(st.X), _p(V), total, stream), "gg_add3")
+        Vb = sh.to_band(V)
+        Tb = torch.empty_like(Vb)
+        _lib.check(lib.gg_prox_band(_p(Vb), _p(Tb), _p(st.ctrl), float(lambda1), float(lambda2), regi, K_total, sh.nb,
+                                    p, sh.r_lo, stream), "gg_prox_band")
+        st.Theta = sh.from_band(Tb)
+        if latent:
+            # C = Theta - X - Omega, L = prox_rank_norm(C)  (per instance, local)
+            torch.sub(st.Theta, st.X, out=st.W)
+            st.W.sub_(st.Omega_new)
+            st.l_step()
+        _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L), _p(st.ctrl),
+                                      K_loc, p, K_loc, 0, _p(partials), stream), "gg_dual_update")
+        torch.sum(partials, 0, keepdim=True, out=tot)
+        sh.allreduce_sum(tot)
+        _lib.check(lib.gg_stop_update(_p(tot), 1, _p(st.ctrl), _p(st.hist), st.hist_cap, _p(st.pdim), tol, rtol,
+                                      1 if update_rho else 0, 1, stream), "gg_stop_update")
+        st.swap()
+        if (it + 1) % check_every == 0 or it + 1 == max_iter:
+            ctrl = st.read_ctrl()
+            if verbose and sh.rank == 0:
+                n = int(ctrl[0, C_ITER])
+                h = st.hist[0, n - 1].cpu().numpy()
+                print("%4d\t%10.4g\t%10.4g\t%10.4g\t%10.4g" % (n - 1, h[0], h[1], h[2], h[3]))
+            if ctrl[0, C_DONE] != 0:
+                break
+    st.finish_x()
+    ctrl = st.read_ctrl()
+    n = int(ctrl[0, C_ITER])
+    hist = st.hist[0, :n].cpu().numpy()
+    r, s, e_pri, e_dual = hist[n - 1, :4]
+    if ctrl[0, C_DONE] != 0:
+        status = "optimal"
+    elif r <= e_pri:
+        status = "primal optimal"
+    elif s <= e_dual:
+        status = "dual optimal"
+    else:
+        status = "max iterations reached"
+    info = {"status": status, "iterations": n, "residual": np.maximum(hist[:, 0], hist[:, 1])}
+    return st, info
+
+
+# ------------------------------------------------------------------------------------------------
+# lambda grid sharding
+# ------------------------------------------------------------------------------------------------
+def ebic_mgl(S, Theta, N, gamma):
+    """extended BIC summed over instances (reference: src/gglasso/helper/model_selection.py:841-869,
+    robust_logdet :884-894: -inf when the smallest eigenvalue is <= 1e-12)."""
+    K, p, _ = S.shape
+    total = 0.0
+    for k in range(K):
+        w = np.linalg.eigvalsh(Theta[k])
+        logdet = np.log(w).sum() if w.min() > 1e-12 else -np.inf
+        E = (np.count_nonzero(Theta[k]) - p) / 2
+        total += N[k] * (np.sum(S[k] * Theta[k]) - logdet) + E * (np.log(N[k]) + 4 * np.log(p) * gamma)
+    return total
+
+
+def grid_search_dist(solver, S, N, reg, l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7, group=None, score=ebic_mgl,
+                     solver_kwargs=None):
+    """lambda1 x lambda2 grid for conforming MGL problems, lambda1 columns dealt round-robin to ranks.
+
+    Mirrors the loop of the reference's ``grid_search`` (columns = lambda1 values run outermost, lambda2
+    innermost, warm start ``Omega_0 <- previous Omega`` inside a column).  Across columns the reference chains
+    the warm start as well; here every column starts from the identity, which changes iteration counts but
+    not the optimum (strictly convex problem) -- SURVEY.md section 7 "grid sharding vs warm-start chain".
+
+    Returns (scores (len(l2), len(l1)), best_index (g1, g2), best_sol) on every rank.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    K, p, _ = S.shape
+    l1 = np.asarray(l1, dtype=float)
+    l2 = np.asarray(l2, dtype=float)
+    scores = np.full((len(l2), len(l1)), np.nan)
+    iters = np.zeros((len(l2), len(l1)), dtype=int)
+    best, best_score, best_ix = None, np.inf, None
+    kw = dict(solver_kwargs or {})
+    for g2 in range(rank, len(l1), world):
+        Omega_0 = np.repeat(np.eye(p)[None], K, 0)
+        for g1 in range(len(l2)):
+            sol, info = solver(S, l1[g2], l2[g1], reg, Omega_0, tol=tol, rtol=rtol, **kw)
+            Omega_0 = sol["Omega"].copy()
+            sc = score(S, sol["Theta"], N, gamma)
+            scores[g1, g2] = sc
+            if sc < best_score:
+                best_score, best_ix, best = sc, (g1, g2), {k: v.copy() for k, v in sol.items()}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (scores, best_score, best_ix), group=group)
+        scores = np.full_like(scores, np.nan)
+        owner, owner_score = 0, np.inf
+        for r, (sc, bs, bix) in enumerate(gathered):
+            m = ~np.isnan(sc)
+            scores[m] = sc[m]
+            if bs < owner_score:
+                owner, owner_score, best_ix = r, bs, bix
+        obj = [best if rank == owner else None]
+        dist.broadcast_object_list(obj, src=owner, group=group)
+        best = obj[0]
+    return scores, best_ix, best
+
+
+def assign_blocks(sizes, world):
+    """longest-processing-time assignment of connected components (cost ~ size^3) to ranks."""
+    order = np.argsort(-np.asarray(sizes, dtype=float) ** 3, kind="stable")
+    load = np.zeros(world)
+    owner = np.zeros(len(sizes), dtype=int)
+    for i in order:
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += float(sizes[i]) ** 3
+    return owner

@@ -9,7 +9,7 @@ from typing import Optional, Union
 
 import numpy as np
 
-from .._engine import run_admm
+from .._engine import run_admm, to_host
 
 
 def ADMM_MGL(S: np.ndarray,
@@ -65,18 +65,17 @@ def ADMM_MGL(S: np.ndarray,
         assert len(nk) == K
 
     if len(Theta_0) == 0:
-        Theta_0 = Omega_0
+        Theta_0 = None          # device-side default: copy of Omega_0
     if len(X_0) == 0:
-        X_0 = np.zeros((K, p, p))
+        X_0 = None              # device-side default: zeros
     # prox_p asserts symmetry of its input (ggl_helper.py:193); with symmetric S and start points the
-    # iterates stay symmetric, so the check is done once on the inputs.
-    for name, A in (("S", S), ("Omega_0", Omega_0), ("Theta_0", Theta_0), ("X_0", X_0)):
-        assert np.abs(A - A.transpose(0, 2, 1)).max() <= 1e-5, "input X is not symmetric"
+    # iterates stay symmetric, so the check is done once on the inputs -- on the device, after the upload
+    # (run_admm(check_symmetric=True)), not with host-side temporaries.
 
     st, res = run_admm('mgl', S, Omega_0, Theta_0, X_0, lambda1=float(lambda1), lambda2=float(lambda2), reg=reg,
                        rho=float(rho), max_iter=int(max_iter), tol=tol, rtol=rtol,
                        stopping_criterion=stopping_criterion, update_rho=update_rho, verbose=verbose,
-                       measure=measure, latent=latent, mu=mu, nk=nk,
+                       measure=measure, latent=latent, mu=mu, nk=nk, check_symmetric=True,
                        header="------------ADMM Algorithm for Multiple Graphical Lasso----------------")
     n_it = int(res["iters"][0])
     status = res["status"][0]
@@ -99,8 +98,8 @@ def ADMM_MGL(S: np.ndarray,
         if st.min_eig(st.L) < -1e-5:
             print("WARNING: L is not positive semidefinite. Solve to higher accuracy!")
 
-    sol = {'Omega': Omega_d.cpu().numpy(), 'Theta': st.Theta.cpu().numpy(),
-           'L': st.L.cpu().numpy() if latent else np.zeros((K, p, p)), 'X': st.X.cpu().numpy()}
+    sol = {'Omega': to_host(Omega_d), 'Theta': to_host(st.Theta),
+           'L': to_host(st.L) if latent else np.zeros((K, p, p)), 'X': to_host(st.X)}
     if measure:
         info = {'status': status,
                 'runtime': res["runtime"][:n_it],

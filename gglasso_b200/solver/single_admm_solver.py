@@ -9,7 +9,7 @@ from typing import Optional
 import numpy as np
 from scipy.sparse.csgraph import connected_components
 
-from .._engine import run_admm
+from .._engine import run_admm, to_host
 
 
 def ADMM_SGL(S: np.ndarray,
@@ -58,9 +58,9 @@ def ADMM_SGL(S: np.ndarray,
     assert rho > 0, "ADMM penalization parameter must be positive."
 
     if len(Theta_0) == 0:
-        Theta_0 = Omega_0
+        Theta_0 = None          # device-side default: copy of Omega_0
     if len(X_0) == 0:
-        X_0 = np.zeros((p, p))
+        X_0 = None              # device-side default: zeros
 
     st, res = run_admm('sgl', S, Omega_0, Theta_0, X_0, lambda1=float(lambda1), lam_mat=lam_mat, rho=float(rho),
                        max_iter=int(max_iter), tol=tol, rtol=rtol, stopping_criterion=stopping_criterion,
@@ -89,9 +89,9 @@ def ADMM_SGL(S: np.ndarray,
         if dmin < -1e-8:
             print(f"WARNING: L is not positive semidefinite. Solve to higher accuracy! (min EV is {dmin})")
 
-    sol = {'Omega': Omega_d[0].cpu().numpy(), 'Theta': st.Theta[0].cpu().numpy(), 'X': st.X[0].cpu().numpy()}
+    sol = {'Omega': to_host(Omega_d[0]), 'Theta': to_host(st.Theta[0]), 'X': to_host(st.X[0])}
     if latent:
-        sol['L'] = st.L[0].cpu().numpy()
+        sol['L'] = to_host(st.L[0])
 
     if measure:
         info = {'status': status, 'runtime': res["runtime"][:n_it], 'residual': res["residual"][0]}

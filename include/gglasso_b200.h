@@ -83,7 +83,14 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
                 double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
                 double* partials, void* stream);
 
-/* X += Omega - Theta + L and partial sums (latent variants)   admm_solver.py:208, single_admm_solver.py:177.
+/* K-sharded MGL (one process per GPU): V = (Omega + L) + X on the local instances
+ * (L may be NULL), and the cross-instance prox on a row band: V, Theta are (K, nb, p) slabs holding global rows
+ * row0..row0+nb-1 of all K instances (after the all-to-all re-tile).  Same prox as gg_prox_mgl. */
+int gg_add3(const double* Omega, const double* L, const double* X, double* V, size_t total, void* stream);
+int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lambda1, double lambda2, int reg,
+                 int K, int nb, int p, int row0, void* stream);
+
+/* X += Omega - Theta + L and partial sums (latent variants; L may be NULL for the K-sharded non-latent loop)   admm_solver.py:208, single_admm_solver.py:177.
  * sgl_order selects the association order of the reference's SGL expression. */
 int gg_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta,
                    const double* L, const double* ctrl, int M, int p, int mpp, int sgl_order,
