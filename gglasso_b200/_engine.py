@@ -93,9 +93,9 @@ class Eigh:
         self.quad_tol = float(os.environ.get("GG_QUAD_TOL", "1e-10"))
         self.sweeps = []
 
-    def eigh(self, A, ctrl=None, mpp=1, vectors=1, stream=0):
+    def eigh(self, A, ctrl=None, mpp=1, vectors=1, stream=0, warm=None):
         rc = self.lib.gg_eigh(_p(A), _p(self.D), self.M, self.p, _p(ctrl), mpp, _p(self.ws), self.ws_bytes,
-                              vectors, self.nb2, 0.0, 0, self.quad_tol, self.info, stream)
+                              vectors, self.nb2, 0.0, 0, self.quad_tol, self.info, _p(warm), stream)
         _lib.check(rc, "gg_eigh")
         self.sweeps.append(self.info[0])
         return self.D
@@ -131,7 +131,8 @@ def eigh(A, nb2=None):
 class AdmmState:
     """Device buffers of one batched ADMM run: M matrices, ``mpp`` per problem."""
 
-    def __init__(self, S, Omega_0, Theta_0, X_0, mpp, rho, max_iter, latent, nk=None, mu=None, lam_mat=None):
+    def __init__(self, S, Omega_0, Theta_0, X_0, mpp, rho, max_iter, latent, nk=None, mu=None, lam_mat=None,
+                 pvec=None):
         self.lib = _lib.load()
         self.dev = dev = require_cuda()
         self.S = to_dev(S, dev)
@@ -149,6 +150,12 @@ class AdmmState:
         self.L = torch.zeros_like(self.S) if latent else None
         self.W = torch.empty_like(self.S)
         self.eig = Eigh(self.M, self.p, dev)
+        # warm start of the small-matrix eigensolver: previous eigenvectors of W (and of C when latent)
+        self.warm_w = self.warm_c = None
+        if self.p <= 160 and os.environ.get("GG_NO_WARM", "0") != "1":
+            eye = torch.eye(self.p, dtype=torch.float64, device=dev)
+            self.warm_w = eye.repeat(self.M, 1, 1).contiguous()
+            self.warm_c = self.warm_w.clone() if latent else None
         self.nk = None if nk is None else to_dev(nk, dev)
         self.mu = None if mu is None else to_dev(mu, dev)
         self.lam_mat = None if lam_mat is None else to_dev(lam_mat, dev)
@@ -159,7 +166,13 @@ class AdmmState:
         self.hist_cap = max_iter
         self.hist = torch.zeros((self.nprob, max_iter, HIST_STRIDE), dtype=torch.float64, device=dev)
         p = self.p
-        self.pdim = to_dev(np.full(self.nprob, mpp * ((p ** 2 + p) / 2)), dev)
+        self.pvec = None
+        if pvec is None:
+            self.pdim = to_dev(np.full(self.nprob, mpp * ((p ** 2 + p) / 2)), dev)
+        else:                               # ragged batch of independent SGL problems padded to p
+            pv = np.asarray(pvec, dtype=np.int64)
+            self.pvec = torch.from_numpy(pv.astype(np.int32)).to(dev)
+            self.pdim = to_dev((pv ** 2 + pv) / 2.0, dev)
         self.stream = torch.cuda.current_stream().cuda_stream
 
     # -- one Omega step: W build, eigh, phi+ reconstruction into Omega_new -----------------
@@ -167,13 +180,13 @@ class AdmmState:
         lib, st = self.lib, self.stream
         _lib.check(lib.gg_build_w(_p(self.Theta), _p(self.L), _p(self.X), _p(self.S), _p(self.nk), _p(self.ctrl),
                                   self.M, self.p, self.mpp, _p(self.W), st), "gg_build_w")
-        self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+        self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st, warm=self.warm_w)
         self.eig.recon(self.W, self.Omega_new, 0, bnum=self.nk, ctrl=self.ctrl, mpp=self.mpp, stream=st)
 
     def l_step(self):
         """latent: W holds C = Theta - X - Omega; L = V max(D - mu/rho, 0) V^T."""
         st = self.stream
-        self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+        self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st, warm=self.warm_c)
         self.eig.recon(self.W, self.L, 1, bnum=self.mu, ctrl=self.ctrl, mpp=self.mpp, stream=st)
 
     def swap(self):
@@ -211,7 +224,7 @@ class AdmmState:
 def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None, lam_mat=None, rho=1.0,
              max_iter=1000, tol=1e-7, rtol=1e-4, stopping_criterion="boyd", update_rho=True, verbose=False,
              measure=False, latent=False, mu=None, nk=None, header=None, check_every=None, trace=None,
-             check_symmetric=False):
+             check_symmetric=False, pvec=None):
     """Run the device ADMM loop.  ``kind``: 'mgl' (one problem of K matrices) or 'sgl' (M problems).
 
     Returns (state, info) where info carries iteration counts, status and histories (numpy).
@@ -221,7 +234,7 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     mpp = M if kind == "mgl" else 1
     st = AdmmState(S3, Omega_0.reshape(S3.shape), None if Theta_0 is None else Theta_0.reshape(S3.shape),
                    None if X_0 is None else X_0.reshape(S3.shape), mpp, rho, max_iter, latent, nk=nk, mu=mu,
-                   lam_mat=lam_mat)
+                   lam_mat=lam_mat, pvec=pvec)
     lib, stream = st.lib, st.stream
     nprob = st.nprob
     regi = {"GGL": 0, "FGL": 1}.get(reg, -1)
@@ -267,8 +280,8 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
                        "gg_prox_mgl")
         else:
             _lib.check(lib.gg_prox_sgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
-                                       _p(st.ctrl), float(lambda1), _p(st.lam_mat), M, p, _p(partials), stream),
-                       "gg_prox_sgl")
+                                       _p(st.ctrl), float(lambda1), _p(st.lam_mat), M, p, _p(partials), _p(st.pvec),
+                                       stream), "gg_prox_sgl")
         if latent:
             st.l_step()
             _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L),
@@ -375,7 +388,7 @@ def _kkt_residual(kind, st, lambda1, lambda2, regi, latent):
                                    lambda2, regi, M, p, None, stream), "gg_prox_mgl")
     else:
         _lib.check(lib.gg_prox_sgl(_p(Theta), _p(Theta), _p(Xu), _p(zero), _p(P), _p(Cdummy), _p(ctrl1),
-                                   float(lambda1), _p(st.lam_mat), M, p, None, stream), "gg_prox_sgl")
+                                   float(lambda1), _p(st.lam_mat), M, p, None, None, stream), "gg_prox_sgl")
     nT = torch.linalg.norm(Theta)
     t1 = torch.linalg.norm(Theta - P) / (1 + nT)
     t2 = torch.linalg.norm(Theta - Omega - L) / (1 + nT)

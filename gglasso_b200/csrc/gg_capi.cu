@@ -6,7 +6,7 @@
 int gg_launch_build_w(const double*, const double*, double*, const double*, const double*, const double*, int, int,
                       int, double*, cudaStream_t);
 int gg_launch_prox_sgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
-                       const double*, int, int, double*, cudaStream_t);
+                       const double*, int, int, double*, const int*, cudaStream_t);
 int gg_launch_dual_update(double*, const double*, const double*, const double*, const double*, const double*, int,
                           int, int, int, double*, cudaStream_t);
 int gg_launch_prox_mgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
@@ -21,7 +21,7 @@ int gg_launch_recon(const double*, const double*, const double*, const double*, 
                     cudaStream_t);
 size_t gg_eigh_ws_bytes(int, int);
 int gg_eigh_impl(double*, double*, int, int, const double*, int, void*, size_t, int, int, double, int, double, int*,
-                 cudaStream_t);
+                 double*, cudaStream_t);
 
 int gg_eigh_tridiag_impl(double*, double*, int, int, const double*, int, void*, size_t, cudaStream_t, int);
 int gg_launch_add3(const double*, const double*, const double*, double*, size_t, cudaStream_t);
@@ -49,11 +49,12 @@ int gg_build_w(const double* Theta, const double* L, double* X, const double* S,
 size_t gg_eigh_workspace_bytes(int M, int p) { return gg_eigh_ws_bytes(M, p); }
 
 int gg_eigh(double* A, double* D, int M, int p, const double* ctrl, int mpp, void* ws, size_t ws_bytes,
-            int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, void* stream)
+            int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, double* Vt_warm,
+            void* stream)
 {
     if (M < 0 || p < 0 || mpp <= 0) return -1;
     return gg_eigh_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, vectors, block_nb2, tol, max_sweeps, quad_tol, info,
-                        (cudaStream_t)stream);
+                        Vt_warm, (cudaStream_t)stream);
 }
 
 int gg_recon(const double* Vt, const double* D, const double* bnum, const double* ctrl, int mpp, int mode, int M,
@@ -64,10 +65,11 @@ int gg_recon(const double* Vt, const double* D, const double* bnum, const double
 }
 
 int gg_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta, double* C,
-                const double* ctrl, double lam, const double* lam_mat, int M, int p, double* partials, void* stream)
+                const double* ctrl, double lam, const double* lam_mat, int M, int p, double* partials, const int* pvec,
+                void* stream)
 {
     if (M <= 0 || p <= 0) return -1;
-    return gg_launch_prox_sgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, M, p, partials,
+    return gg_launch_prox_sgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, M, p, partials, pvec,
                               (cudaStream_t)stream);
 }
 

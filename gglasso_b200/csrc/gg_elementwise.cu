@@ -68,12 +68,14 @@ __global__ void __launch_bounds__(EW_THREADS)
 prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Omega_prev,
                 const double* __restrict__ L, double* __restrict__ X, double* __restrict__ Theta,
                 double* __restrict__ C, const double* __restrict__ ctrl, double lam,
-                const double* __restrict__ lam_mat, int p, double* __restrict__ partials)
+                const double* __restrict__ lam_mat, int p, double* __restrict__ partials,
+                const int* __restrict__ pvec)
 {
     __shared__ double scratch[GG_NPART * 32];
     const int m = blockIdx.y;
     const double* c = ctrl + (size_t)m * GG_CTRL_STRIDE;
     if (c[GG_C_DONE] != 0.0) return;
+    const int pb = pvec ? pvec[m] : p;       // ragged batches: entries beyond pb are padding, excluded from norms
     const double inv_rho = 1.0 / c[GG_C_RHO];
     const size_t pp = (size_t)p * p;
     const size_t base = (size_t)m * pp;
@@ -95,8 +97,10 @@ prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
         } else {
             const double xn = (x + om) - th;      // X_t + Omega_t - Theta_t (+ L_t = 0)
             X[base + e] = xn;
-            const double d1 = om - th, d2 = om - Omega_prev[base + e];
-            acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+            if (i < pb && j < pb) {
+                const double d1 = om - th, d2 = om - Omega_prev[base + e];
+                acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+            }
         }
     }
     if (!C) {
@@ -440,10 +444,11 @@ extern "C" int gg_sgl_nparts(int p, int M) { return ew_blocks((size_t)p * p, M);
 
 int gg_launch_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
                        double* C, const double* ctrl, double lam, const double* lam_mat, int M, int p,
-                       double* partials, cudaStream_t st)
+                       double* partials, const int* pvec, cudaStream_t st)
 {
     dim3 grid(gg_sgl_nparts(p, M), M);
-    prox_sgl_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, p, partials);
+    prox_sgl_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, p, partials,
+                                                 pvec);
     GG_CHECK_LAUNCH();
     return 0;
 }

@@ -24,9 +24,14 @@
 // ==========================================================================================
 // small path: one CTA per matrix, everything in shared memory
 // ==========================================================================================
+// Vwarm (optional, (M,p,p), rows = orthonormal vectors): ADMM-aware warm start.  The iterates change slowly,
+// so the previous iteration's eigenvectors nearly diagonalise the new matrix: starting the row
+// orthogonalisation from G = Vwarm * A_s instead of A_s cuts the sweeps from ~9 to 2-4.  On exit Vwarm is
+// overwritten by the new eigenvectors.
 __global__ void __launch_bounds__(JS_THREADS)
 jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, double tol, int max_sweeps,
-                    const double* __restrict__ ctrl, int mpp, int* __restrict__ sweeps_out)
+                    const double* __restrict__ ctrl, int mpp, int* __restrict__ sweeps_out,
+                    double* __restrict__ Vwarm)
 {
     extern __shared__ double G[];            // p x ld
     __shared__ double red[64];
@@ -35,16 +40,17 @@ jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, doubl
     if (ctrl && ctrl[(size_t)(m / mpp) * GG_CTRL_STRIDE + GG_C_DONE] != 0.0) return;
     const int ld = p | 1;
     double* Am = A + (size_t)m * p * p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
-        const int i = e / p, j = e - i * p;
-        G[i * ld + j] = Am[e];
+        const int i = e / p, jj = e - i * p;
+        G[i * ld + jj] = Am[e];
     }
     __syncthreads();
     // Gershgorin bounds
     double lo = 1.0e300, hi = -1.0e300;
     for (int i = threadIdx.x; i < p; i += blockDim.x) {
         double rs = 0.0;
-        for (int j = 0; j < p; ++j) rs += fabs(G[i * ld + j]);
+        for (int jj = 0; jj < p; ++jj) rs += fabs(G[i * ld + jj]);
         const double d = G[i * ld + i];
         rs -= fabs(d);
         lo = fmin(lo, d - rs);
@@ -62,7 +68,21 @@ jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, doubl
     }
     __syncthreads();
     const double sigma = s_sigma;
-    for (int i = threadIdx.x; i < p; i += blockDim.x) G[i * ld + i] += sigma;
+    if (Vwarm == nullptr) {
+        for (int i = threadIdx.x; i < p; i += blockDim.x) G[i * ld + i] += sigma;
+    } else {
+        // G <- Vwarm * (A + sigma I); A is re-read from global/L1 (the shared copy is being overwritten)
+        const double* Vw = Vwarm + (size_t)m * p * p;
+        __syncthreads();
+        for (int o = threadIdx.x; o < p * p; o += blockDim.x) {
+            const int c = o / p, jj = o - c * p;
+            const double* vr = Vw + (size_t)c * p;
+            double acc = sigma * vr[jj];
+#pragma unroll 4
+            for (int k = 0; k < p; ++k) acc = fma(vr[k], Am[(size_t)k * p + jj], acc);
+            G[c * ld + jj] = acc;
+        }
+    }
     __syncthreads();
 
     const int sw = jacobi_rows_smem<8>(G, p, ld, tol, max_sweeps);
@@ -70,7 +90,7 @@ jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, doubl
     __syncthreads();
 
     // finalise: lambda_i = |g_i| - sigma ; v_i = g_i / |g_i|
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* Vw = Vwarm ? Vwarm + (size_t)m * p * p : nullptr;
     for (int i = wid; i < p; i += nw) {
         double ss = 0.0;
         for (int e = lane; e < p; e += 32) { const double x = G[i * ld + e]; ss = fma(x, x, ss); }
@@ -78,7 +98,11 @@ jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, doubl
         const double nrm = sqrt(ss);
         const double inv = 1.0 / nrm;
         if (lane == 0) D[(size_t)m * p + i] = nrm - sigma;
-        for (int e = lane; e < p; e += 32) Am[(size_t)i * p + e] = G[i * ld + e] * inv;
+        for (int e = lane; e < p; e += 32) {
+            const double v = G[i * ld + e] * inv;
+            Am[(size_t)i * p + e] = v;
+            if (Vw) Vw[(size_t)i * p + e] = v;
+        }
     }
 }
 
@@ -421,7 +445,7 @@ static int launch_round(double* G, int M, int p, int nb, int round, double tol, 
 // D: (M,p) eigenvalues (unsorted).  info[0] = sweeps used (block path) / max sweeps (small path).
 int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp, void* ws, size_t ws_bytes,
                  int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info,
-                 cudaStream_t s)
+                 double* Vwarm, cudaStream_t s)
 {
     if (M <= 0 || p <= 0) return 0;
     if (ws_bytes < gg_jacobi_ws_bytes(M, p)) return -3;
@@ -449,7 +473,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
             if (e != cudaSuccess) return (int)e;
             attr = true;
         }
-        jacobi_small_kernel<<<M, JS_THREADS, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small);
+        jacobi_small_kernel<<<M, JS_THREADS, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
         GG_CHECK_LAUNCH();
         if (info) info[0] = 0;
         return 0;

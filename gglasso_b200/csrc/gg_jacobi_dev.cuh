@@ -48,10 +48,13 @@ __device__ int jacobi_rows_smem(double* G, int n, int ld, double tol, int max_sw
                     b += __shfl_xor_sync(0xffffffffu, b, o);
                     g += __shfl_xor_sync(0xffffffffu, g, o);
                 }
-                if (act && fabs(g) > tol * sqrt(a * b)) {
-                    const double zeta = (b - a) / (2.0 * g);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = rsqrt(1.0 + t * t);
+                if (act && g * g > (tol * tol) * (a * b)) {
+                    // tan(theta) = 2g sign(d) / (|d| + sqrt(d^2 + 4g^2)), d = b - a   (smaller root; one sqrt,
+                    // one division, one rsqrt -- these FP64 chains dominate the latency of a round)
+                    const double dd = b - a;
+                    const double hh = sqrt(fma(dd, dd, 4.0 * g * g));
+                    const double t = copysign(2.0 * g, dd * g) / (fabs(dd) + hh);
+                    const double c = rsqrt(fma(t, t, 1.0));
                     const double sn = c * t;
                     double* gi = G + (size_t)i * ld;
                     double* gj = G + (size_t)j * ld;

@@ -47,6 +47,8 @@ tr_col_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restri
     __shared__ double red[64];
     __shared__ double s_bc[4];
     const int m = blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
     if (skip && skip[m]) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     double* Am = A + (size_t)m * n * n;
@@ -126,12 +128,14 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restr
     __shared__ double tile[SV_T][SV_T + 1];
     __shared__ double s_vpI[SV_T], s_wI[SV_T], s_vI[SV_T], s_vpJ[SV_T], s_wJ[SV_T], s_vJ[SV_T];
     const int m = blockIdx.y;
-    if (skip && skip[m]) return;
     const int t = n - j - 1;
     const int base = j + 1;
     int idx = blockIdx.x, I = 0;
     while (idx >= nt - I) { idx -= nt - I; ++I; }
     const int J = I + idx;
+    asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
+    if (skip && skip[m]) return;
     const int r0 = I * SV_T, c0 = J * SV_T;
     const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n + base;
     const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
@@ -891,13 +895,29 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     GG_CHECK_LAUNCH();
 
     // ---- stage 1 ----
-    for (int j = 0; j < n; ++j) {
-        if (which != 2) tr_col_kernel<<<M, 1024, 0, s>>>(A, n, j, tw, skip);
-        if (j < n - 1 && which != 1) {
-            const int t = n - j - 1;
-            const int nt = (t + SV_T - 1) / SV_T;
-            dim3 g(nt * (nt + 1) / 2, M);
-            tr_symv_kernel<<<g, 256, 0, s>>>(A, n, j, tw, skip, nt);
+    {
+        // the 2p-1 launches of this chain are short and strictly dependent: programmatic dependent launch
+        // lets launch k+1 be set up while launch k drains (kernels start with griddepcontrol.wait)
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.stream = s;
+        cfg.attrs = pdl;
+        cfg.numAttrs = 1;
+        for (int j = 0; j < n; ++j) {
+            if (which != 2) {
+                cfg.gridDim = dim3(M); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0;
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_col_kernel, A, n, j, tw, (const int*)skip);
+                if (e != cudaSuccess) return (int)e;
+            }
+            if (j < n - 1 && which != 1) {
+                const int t = n - j - 1;
+                const int nt = (t + SV_T - 1) / SV_T;
+                cfg.gridDim = dim3(nt * (nt + 1) / 2, M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, tw, (const int*)skip, nt);
+                if (e != cudaSuccess) return (int)e;
+            }
         }
     }
     GG_CHECK_LAUNCH();

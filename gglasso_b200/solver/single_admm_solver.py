@@ -3,6 +3,8 @@
 Same signatures, defaults, asserts, printed lines, return dicts and status strings as the reference
 (src/gglasso/solver/single_admm_solver.py:15-275 and :326-498); the iteration runs as CUDA kernels.
 """
+import contextlib
+import io
 import warnings
 from typing import Optional
 
@@ -144,25 +146,87 @@ def block_SGL(S: np.ndarray,
     numC, allC = get_connected_components(S, lambda1 * lambda1_mask)
 
     sol = {'Omega': np.zeros((p, p)), 'Theta': np.zeros((p, p)), 'X': np.zeros((p, p))}
-    for C in allC:
-        ix = np.ix_(C, C)
+    kw = dict(tol=tol, rtol=rtol, stopping_criterion=stopping_criterion, update_rho=update_rho, rho=rho,
+              max_iter=max_iter, verbose=verbose, measure=measure)
+    lines = {}
+    multi = [ci for ci, C in enumerate(allC) if len(C) > 1]
+    for ci, C in enumerate(allC):
         if len(C) == 1:
             # single node components have a closed form solution (off-diagonal penalty only)
             closed_sol = 1 / S[C, C]
-            sol['Omega'][ix] = closed_sol
-            sol['Theta'][ix] = closed_sol
-        else:
+            sol['Omega'][C, C] = closed_sol
+            sol['Theta'][C, C] = closed_sol
+
+    # Components that fit the shared-memory eigensolver are solved as ragged batches (one CTA per block and
+    # kernel, per-block rho / stopping test on the device); larger ones one by one on the large-p path.
+    batchable = stopping_criterion == "boyd" and not verbose and not measure
+    small = [ci for ci in multi if len(allC[ci]) <= _BATCH_MAX] if batchable else []
+    large = [ci for ci in multi if ci not in set(small)]
+    for bucket in _size_buckets([len(allC[ci]) for ci in small]):
+        ids = [small[k] for k in bucket]
+        _solve_batch(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, [allC[ci] for ci in ids], ids, sol, lines, kw)
+    for ci in large:
+        C = allC[ci]
+        ix = np.ix_(C, C)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
             block_sol, _ = ADMM_SGL(S=np.ascontiguousarray(S[ix]),
                                     lambda1=lambda1,
                                     Omega_0=np.ascontiguousarray(Omega_0[ix]),
                                     Theta_0=np.ascontiguousarray(Theta_0[ix]),
                                     X_0=np.ascontiguousarray(X_0[ix]),
-                                    tol=tol, rtol=rtol, stopping_criterion=stopping_criterion,
-                                    update_rho=update_rho, rho=rho, max_iter=max_iter, verbose=verbose,
-                                    measure=measure, lambda1_mask=np.ascontiguousarray(lambda1_mask[ix]))
-            for k in sol:
-                sol[k][ix] = block_sol[k]
+                                    lambda1_mask=np.ascontiguousarray(lambda1_mask[ix]), **kw)
+        lines[ci] = buf.getvalue()
+        for k in sol:
+            sol[k][ix] = block_sol[k]
+    # the reference prints one termination line per non-trivial block, in component order
+    for ci in multi:
+        print(lines[ci], end="")
     return sol
+
+
+_BATCH_MAX = 160          # GG_SMALL_MAX of the eigensolver
+
+
+def _size_buckets(sizes):
+    """group indices of blocks by padded size: powers of two up to 32, then steps of 32 (bounded padding waste)."""
+    edges = [2, 4, 8, 16, 32, 64, 96, 128, 160]
+    buckets = {}
+    for k, s in enumerate(sizes):
+        e = next(x for x in edges if s <= x)
+        buckets.setdefault(e, []).append(k)
+    return [buckets[e] for e in sorted(buckets)]
+
+
+def _solve_batch(S, lambda1, mask, Omega_0, Theta_0, X_0, comps, ids, sol, lines, kw):
+    """one ragged batch: blocks padded to the largest size with decoupled unit diagonal entries (S=Omega=Theta=1,
+    X=0 there: exact fixed points of the iteration for every rho, excluded from the norms through pvec)."""
+    M = len(comps)
+    pm = max(len(C) for C in comps)
+    eye = np.eye(pm)
+    Sb = np.repeat(eye[None], M, 0)
+    Ob, Tb, Xb = Sb.copy(), Sb.copy(), np.zeros((M, pm, pm))
+    Lb = np.zeros((M, pm, pm))
+    for b, C in enumerate(comps):
+        n = len(C)
+        ix = np.ix_(C, C)
+        Sb[b, :n, :n] = S[ix]
+        Ob[b, :n, :n] = Omega_0[ix]
+        Tb[b, :n, :n] = Theta_0[ix]
+        Xb[b, :n, :n] = X_0[ix]
+        Lb[b, :n, :n] = lambda1 * mask[ix]
+    st, res = run_admm('sgl', Sb, Ob, Tb, Xb, lambda1=float(lambda1), lam_mat=Lb, rho=float(kw["rho"]),
+                       max_iter=int(kw["max_iter"]), tol=kw["tol"], rtol=kw["rtol"], update_rho=kw["update_rho"],
+                       pvec=[len(C) for C in comps])
+    Om = to_host(st.final_omega(res["iters"]))
+    Th, Xs = to_host(st.Theta), to_host(st.X)
+    for b, (C, ci) in enumerate(zip(comps, ids)):
+        n = len(C)
+        ix = np.ix_(C, C)
+        sol['Omega'][ix] = Om[b, :n, :n]
+        sol['Theta'][ix] = Th[b, :n, :n]
+        sol['X'][ix] = Xs[b, :n, :n]
+        lines[ci] = f"ADMM terminated after {int(res['iters'][b])} iterations with status: {res['status'][b]}.\n"
 
 
 def get_connected_components(S, lambda1):

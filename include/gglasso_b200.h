@@ -46,10 +46,13 @@ int gg_build_w(const double* Theta, const double* L, double* X, const double* S,
  * eigenvector belonging to D[m][c] (order and signs arbitrary).  vectors=0 skips normalisation
  * (eigenvalues only).  block_nb2 in {0,32,64,128}: rows per block pair of the large-p path (0 = default).
  * tol<=0, max_sweeps<=0: defaults.  quad_tol: a sweep whose largest measured off-diagonal cosine is
- * below quad_tol is taken as the last one (quadratic convergence); 0 disables.  info[0] (host) = sweeps. */
+ * below quad_tol is taken as the last one (quadratic convergence); 0 disables.  info[0] (host) = sweeps.
+ * Vt_warm (optional, (M,p,p), rows orthonormal; used for p <= 160): warm start from the eigenvectors of the
+ * previous ADMM iteration (identity for the first call); overwritten with the new eigenvectors. */
 size_t gg_eigh_workspace_bytes(int M, int p);
 int gg_eigh(double* A, double* D, int M, int p, const double* ctrl, int mpp, void* ws, size_t ws_bytes,
-            int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, void* stream);
+            int vectors, int block_nb2, double tol, int max_sweeps, double quad_tol, int* info, double* Vt_warm,
+            void* stream);
 
 /* Stage 1 of the large-p eigensolver only (Householder tridiagonalisation of the batch), for profiling:
  * which = 0 full sytrd, 1 only the per-column kernels, 2 only the trailing-matrix (symv + rank-2 update)
@@ -68,11 +71,13 @@ int gg_recon(const double* Vt, const double* D, const double* bnum, const double
  * single_admm_solver.py:169.  lam_mat (M,p,p) optional elementwise penalty (lambda1*lambda1_mask).
  * C == NULL (non-latent): fused with X += Omega - Theta (single_admm_solver.py:177) and the partial
  * sums for gg_stop_update (partials: M * gg_sgl_nparts(p,M) * GG_NPART doubles).
- * C != NULL (latent): writes C = Theta - X - Omega (single_admm_solver.py:173), X untouched. */
+ * C != NULL (latent): writes C = Theta - X - Omega (single_admm_solver.py:173), X untouched.
+ * pvec (optional, device int[M]): true size of problem m inside a padded (M,p,p) ragged batch (block_SGL's
+ * connected components, single_admm_solver.py:441-459); entries beyond it are excluded from the norms. */
 int gg_sgl_nparts(int p, int M);
 int gg_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
                 double* C, const double* ctrl, double lam, const double* lam_mat, int M, int p,
-                double* partials, void* stream);
+                double* partials, const int* pvec, void* stream);
 
 /* Theta = prox_p(Omega + L + X, lambda1/rho, lambda2/rho, reg)   src/gglasso/solver/ggl_helper.py:190-207
  * reg 0 = GGL (ggl_helper.py:68-71,38-43), 1 = FGL (ggl_helper.py:131-134, fgl_helper.py:11-68).

@@ -198,7 +198,7 @@ def test_prox_sgl_kernel(p, masked):
     Th = torch.empty_like(dOm)
     lam_mat = to_dev(lam * mask, dev) if masked else None
     assert lib.gg_prox_sgl(_p(dOm), _p(dOmp), None, _p(dX), _p(Th), None, _p(ctrl), lam, _p(lam_mat), M, p,
-                           _p(parts), 0) == 0
+                           _p(parts), None, 0) == 0
     got, gotX = Th.cpu().numpy(), dX.cpu().numpy()
     sums = parts.sum(1).cpu().numpy()
     for m in range(M):
@@ -401,3 +401,51 @@ def test_k_sharded_two_ranks_nccl():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert "DIST_CHECK_OK" in o.stdout, o.stdout[-2000:] + o.stderr[-2000:]
+
+
+def test_block_sgl_ragged_batches_vs_oracle():
+    """many components of different sizes (singletons, 2..45, one > 160): batched ragged solves, per-block rho and
+    stopping test on the device, must reproduce the per-block sequential oracle."""
+    from gglasso_b200 import block_SGL, get_connected_components
+    from oracle import admm_oracle as orc
+    rng = np.random.default_rng(42)
+    sizes = [1, 1, 2, 2, 3, 5, 5, 8, 13, 17, 21, 33, 45, 170, 1, 4]
+    p = sum(sizes)
+    S = np.zeros((p, p))
+    o = 0
+    for s in sizes:
+        Z = rng.standard_normal((s, 3 * s + 5))
+        B = Z @ Z.T / (3 * s + 5)
+        B = B / np.sqrt(np.outer(np.diag(B), np.diag(B)))
+        S[o:o + s, o:o + s] = 0.6 * B + 0.4 * np.eye(s)
+        o += s
+    perm = rng.permutation(p)
+    S = S[np.ix_(perm, perm)]
+    lam = 0.02
+    numC, comps = get_connected_components(S, lam)
+    assert numC >= 10 and max(len(c) for c in comps) > 160
+    (sol, out) = _quiet(block_SGL, S, lam, np.eye(p), tol=1e-8, rtol=1e-8)
+    ref = orc.block_sgl(S, lam, np.eye(p), tol=1e-8, rtol=1e-8)
+    for k in ("Theta", "Omega", "X"):
+        assert np.linalg.norm(sol[k] - ref[k]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(ref[k])), k
+    assert np.array_equal(sol["Theta"] != 0, ref["Theta"] != 0)
+    assert out.count("ADMM terminated after") == sum(1 for c in comps if len(c) > 1)
+
+
+def test_block_sgl_with_mask_and_warm_start_arrays():
+    from gglasso_b200 import block_SGL
+    from oracle import admm_oracle as orc
+    rng = np.random.default_rng(3)
+    p = 60
+    A = rng.standard_normal((p, 4 * p))
+    S = A @ A.T / (4 * p)
+    S[np.abs(S) < 0.12] = 0.0
+    S = (S + S.T) / 2 + 0.5 * np.eye(p)
+    mask = np.ones((p, p))
+    mask[:10, :10] = 2.0
+    Om0 = np.eye(p) * 1.5
+    X0 = np.zeros((p, p))
+    sol, _ = _quiet(block_SGL, S, 0.1, Om0, Theta_0=np.eye(p), X_0=X0, tol=1e-8, rtol=1e-8, lambda1_mask=mask)
+    ref = orc.block_sgl(S, 0.1, Om0, Theta_0=np.eye(p), X_0=X0, tol=1e-8, rtol=1e-8, lambda1_mask=mask)
+    for k in ("Theta", "Omega", "X"):
+        assert np.linalg.norm(sol[k] - ref[k]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(ref[k])), k
