@@ -19,7 +19,8 @@
 #include "gg_jacobi_dev.cuh"
 
 #define GG_SMALL_MAX 160
-#define JS_THREADS 512
+#define JS_THREADS 1024
+#define JS_LP 16
 
 // ==========================================================================================
 // small path: one CTA per matrix, everything in shared memory
@@ -28,6 +29,7 @@
 // so the previous iteration's eigenvectors nearly diagonalise the new matrix: starting the row
 // orthogonalisation from G = Vwarm * A_s instead of A_s cuts the sweeps from ~9 to 2-4.  On exit Vwarm is
 // overwritten by the new eigenvectors.
+template <int NE>
 __global__ void __launch_bounds__(JS_THREADS)
 jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, double tol, int max_sweeps,
                     const double* __restrict__ ctrl, int mpp, int* __restrict__ sweeps_out,
@@ -85,7 +87,7 @@ jacobi_small_kernel(double* __restrict__ A, double* __restrict__ D, int p, doubl
     }
     __syncthreads();
 
-    const int sw = jacobi_rows_smem<8>(G, p, ld, tol, max_sweeps);
+    const int sw = jacobi_rows_smem<JS_LP, NE>(G, p, ld, tol, max_sweeps);
     if (threadIdx.x == 0 && sweeps_out) sweeps_out[m] = sw;
     __syncthreads();
 
@@ -290,7 +292,7 @@ bj_round_kernel(double* __restrict__ G, int p, int nb, int round, double tol, do
     __syncthreads();
     if (s_skip) return;
 
-    jacobi_rows_smem<8>(Hs, NB2, LDH, tol_in, inner_max_sweeps);
+    jacobi_rows_smem<8, NB2 / 8>(Hs, NB2, LDH, tol_in, inner_max_sweeps);
     __syncthreads();
     // rows of Hs are now sigma_i * u_i ; normalise -> Ut (row i = eigenvector i). Zero rows -> e_i.
     for (int i = wid; i < NB2; i += 8) {
@@ -467,19 +469,34 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
         const int ld = p | 1;
         const size_t smem = sizeof(double) * (size_t)p * ld;
         static bool attr = false;
+        const int maxsm = (int)(sizeof(double) * GG_SMALL_MAX * (GG_SMALL_MAX | 1));
         if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(jacobi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(sizeof(double) * GG_SMALL_MAX * (GG_SMALL_MAX | 1)));
+            cudaFuncSetAttribute(jacobi_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+            cudaFuncSetAttribute(jacobi_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+            cudaFuncSetAttribute(jacobi_small_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+            cudaFuncSetAttribute(jacobi_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+            cudaError_t e = cudaFuncSetAttribute(jacobi_small_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
             if (e != cudaSuccess) return (int)e;
             attr = true;
         }
-        jacobi_small_kernel<<<M, JS_THREADS, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
+        // threads: 16 lanes per row pair; no more groups than pairs (rounded up to a warp multiple)
+        int threads = ((p + 1) / 2) * JS_LP;
+        threads = (threads + 31) / 32 * 32;
+        if (threads > JS_THREADS) threads = JS_THREADS;
+        if (threads < 64) threads = 64;
+        const int ne = (p + JS_LP - 1) / JS_LP;
+        if (ne <= 2) jacobi_small_kernel<2><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
+        else if (ne <= 4) jacobi_small_kernel<4><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
+        else if (ne <= 6) jacobi_small_kernel<6><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
+        else if (ne <= 8) jacobi_small_kernel<8><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
+        else jacobi_small_kernel<10><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
         GG_CHECK_LAUNCH();
         if (info) info[0] = 0;
         return 0;
     }
 
     // ---- large p: tridiagonalisation + divide & conquer (default), or block Jacobi on request ----
+    if (block_nb2 != 32 && block_nb2 != 64 && block_nb2 != 128 && p > 7000) block_nb2 = 64;   // D&C smem limit
     if (block_nb2 != 32 && block_nb2 != 64 && block_nb2 != 128) {
         const int rc = gg_eigh_tridiag_impl(A, D, M, p, ctrl, mpp, ws, ws_bytes, s, vectors ? 0 : 4);
         if (info) info[0] = -1;

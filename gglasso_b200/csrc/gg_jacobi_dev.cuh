@@ -12,14 +12,20 @@ __device__ __forceinline__ void rr_pair(int n, int r, int s, int& a, int& b)
 }
 
 // ---- shared-memory one-sided Jacobi on the rows of G (n x n, row stride ld) --------------------
-// LP lanes cooperate on one row pair.  Returns the number of sweeps executed.
-template <int LP>
+// LP lanes cooperate on one row pair; every lane keeps its NE = ceil(n/LP) elements of both rows in registers
+// between the dot-product and the rotation phase (one shared-memory read and one write per element and
+// rotation).  LP = 16 makes every half-warp access one contiguous 128-byte row segment (conflict free).
+// The three dot products run on two accumulators each to halve the dependent FP64 chains, which -- not
+// throughput -- bound this latency-limited kernel (ncu: 41 % short-scoreboard, 23 % barrier stalls).
+// Returns the number of sweeps executed.
+template <int LP, int NE>
 __device__ int jacobi_rows_smem(double* G, int n, int ld, double tol, int max_sweeps)
 {
     const int nn = n + (n & 1);
     const int half = nn >> 1;
     const int ngroups = blockDim.x / LP;
     const int gid = threadIdx.x / LP, gl = threadIdx.x % LP;
+    const double tol2 = tol * tol;
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         int rot = 0;
@@ -33,35 +39,46 @@ __device__ int jacobi_rows_smem(double* G, int n, int ld, double tol, int max_sw
                     if (i > j) { const int t = i; i = j; j = t; }
                     act = j < n;
                 }
-                double a = 0.0, b = 0.0, g = 0.0;
-                if (act) {
-                    const double* gi = G + (size_t)i * ld;
-                    const double* gj = G + (size_t)j * ld;
-                    for (int e = gl; e < n; e += LP) {
-                        const double x = gi[e], y = gj[e];
-                        a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+                double x[NE], y[NE];
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, g0 = 0.0, g1 = 0.0;
+                double* gi = G + (size_t)i * ld;
+                double* gj = G + (size_t)j * ld;
+#pragma unroll
+                for (int q = 0; q < NE; ++q) {
+                    const int e = gl + q * LP;
+                    const bool ok = act && e < n;
+                    x[q] = ok ? gi[e] : 0.0;
+                    y[q] = ok ? gj[e] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < NE; q += 2) {
+                    a0 = fma(x[q], x[q], a0); b0 = fma(y[q], y[q], b0); g0 = fma(x[q], y[q], g0);
+                    if (q + 1 < NE) {
+                        a1 = fma(x[q + 1], x[q + 1], a1); b1 = fma(y[q + 1], y[q + 1], b1);
+                        g1 = fma(x[q + 1], y[q + 1], g1);
                     }
                 }
+                double a = a0 + a1, b = b0 + b1, g = g0 + g1;
 #pragma unroll
                 for (int o = LP >> 1; o > 0; o >>= 1) {
                     a += __shfl_xor_sync(0xffffffffu, a, o);
                     b += __shfl_xor_sync(0xffffffffu, b, o);
                     g += __shfl_xor_sync(0xffffffffu, g, o);
                 }
-                if (act && g * g > (tol * tol) * (a * b)) {
-                    // tan(theta) = 2g sign(d) / (|d| + sqrt(d^2 + 4g^2)), d = b - a   (smaller root; one sqrt,
-                    // one division, one rsqrt -- these FP64 chains dominate the latency of a round)
+                if (act && g * g > tol2 * (a * b)) {
+                    // tan(theta) = 2g sign(d) / (|d| + sqrt(d^2 + 4g^2)), d = b - a   (smaller root)
                     const double dd = b - a;
                     const double hh = sqrt(fma(dd, dd, 4.0 * g * g));
                     const double t = copysign(2.0 * g, dd * g) / (fabs(dd) + hh);
                     const double c = rsqrt(fma(t, t, 1.0));
                     const double sn = c * t;
-                    double* gi = G + (size_t)i * ld;
-                    double* gj = G + (size_t)j * ld;
-                    for (int e = gl; e < n; e += LP) {
-                        const double x = gi[e], y = gj[e];
-                        gi[e] = c * x - sn * y;
-                        gj[e] = sn * x + c * y;
+#pragma unroll
+                    for (int q = 0; q < NE; ++q) {
+                        const int e = gl + q * LP;
+                        if (e < n) {
+                            gi[e] = c * x[q] - sn * y[q];
+                            gj[e] = sn * x[q] + c * y[q];
+                        }
                     }
                     rot = 1;
                 }
@@ -72,4 +89,3 @@ __device__ int jacobi_rows_smem(double* G, int n, int ld, double tol, int max_sw
     }
     return sweep;
 }
-

@@ -208,6 +208,10 @@ struct DcWs {
     double* wnd;      // (M,n) their z components
     double* zhat;     // (M,n)
     int* ndrow;       // (M,n) global row of the i-th non-deflated vector
+    double* rotc;     // (M,n) Givens rotations of the deflation step (cos, sin, row pair)
+    double* rots;     // (M,n)
+    int* rotp;        // (M,n)
+    int* rotn;        // (M,n)
     int* nodek;       // (M,nodes_max) number of non-deflated
     double* noderho;  // (M,nodes_max)
     double* U;        // (M,n,n) Delta / eigenvector matrices, block diagonal like Qt
@@ -310,7 +314,7 @@ dc_leaf_kernel(const double* __restrict__ d, const double* __restrict__ e, int n
     const double sigma = s_sigma;
     if (threadIdx.x < sz) G[threadIdx.x * ld + threadIdx.x] += sigma;
     __syncthreads();
-    jacobi_rows_smem<8>(G, sz, ld, 4.0e-15, 40);
+    jacobi_rows_smem<8, DC_LEAF / 8>(G, sz, ld, 4.0e-15, 40);
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int r = wid; r < sz; r += 4) {
@@ -328,7 +332,7 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
                   double* __restrict__ lam_out, double* __restrict__ Qin, double* __restrict__ Qout, DcWs ws,
                   const int* __restrict__ skip)
 {
-    extern __shared__ double sm[];             // d[N], z[N], then ints idx[N], dfl[N], rots
+    extern __shared__ double sm[];             // d[N], z[N], then ints idx[N], nd[N], df[N]
     const int m = blockIdx.y;
     if (skip && skip[m]) return;
     const int node = blockIdx.x;
@@ -336,13 +340,13 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
     const int N = hi - lo, n1 = mid - lo;
     double* sd = sm;
     double* sz = sm + N;
-    double* rc = sm + 2 * N;                   // rotation cos
-    double* rs = sm + 3 * N;                   // rotation sin
-    int* idx = (int*)(sm + 4 * N);
+    int* idx = (int*)(sm + 2 * N);
     int* nd = idx + N;
     int* df = nd + N;
-    int* rp = df + N;
-    int* rn = rp + N;
+    double* rc = ws.rotc + (size_t)m * n + lo;  // rotation lists live in global memory (only thread 0 writes)
+    double* rs = ws.rots + (size_t)m * n + lo;
+    int* rp = ws.rotp + (size_t)m * n + lo;
+    int* rn = ws.rotn + (size_t)m * n + lo;
     __shared__ int s_k, s_ndf, s_nrot;
     __shared__ double s_rho;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -404,6 +408,7 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
         ws.noderho[(size_t)m * ws.nodes_max + node] = rho;
     }
     __syncthreads();
+    __threadfence_block();
     const int k = s_k, ndf = s_ndf, nrot = s_nrot;
     // Givens rotations on row pairs (in order; chains share rows)
     for (int r = 0; r < nrot; ++r) {
@@ -840,7 +845,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += 3 * al(sizeof(double) * M * nn);                 // Vh, Q0, U
     b += 12 * al(sizeof(double) * Mn);                    // tau d e vbuf(2) w y lam0 lam1 z dl wnd zhat (13) -> see below
     b += 2 * al(sizeof(double) * Mn);
-    b += al(sizeof(int) * Mn);                            // ndrow
+    b += 3 * al(sizeof(int) * Mn) + 2 * al(sizeof(double) * Mn);   // ndrow, rotp, rotn, rotc, rots
     b += al(sizeof(int) * (size_t)M * (1 << L));          // nodek
     b += al(sizeof(double) * (size_t)M * (1 << L));       // noderho
     b += al(sizeof(double) * (size_t)M * npanels * BT_NB * BT_NB);
@@ -877,6 +882,10 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     dw.wnd = (double*)take(sizeof(double) * Mn);
     dw.zhat = (double*)take(sizeof(double) * Mn);
     dw.ndrow = (int*)take(sizeof(int) * Mn);
+    dw.rotc = (double*)take(sizeof(double) * Mn);
+    dw.rots = (double*)take(sizeof(double) * Mn);
+    dw.rotp = (int*)take(sizeof(int) * Mn);
+    dw.rotn = (int*)take(sizeof(int) * Mn);
     dw.nodes_max = 1 << L;
     dw.nodek = (int*)take(sizeof(int) * (size_t)M * dw.nodes_max);
     dw.noderho = (double*)take(sizeof(double) * (size_t)M * dw.nodes_max);
@@ -945,7 +954,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     for (int l = L - 1; l >= 0; --l) {
         const int nodes = 1 << l;
         const int Nmax = ((n + nodes - 1) >> l) + 1;
-        const size_t psm = sizeof(double) * 4 * Nmax + sizeof(int) * 5 * Nmax;
+        const size_t psm = sizeof(double) * 2 * Nmax + sizeof(int) * 3 * Nmax + 16;
         if (psm > 200 * 1024) return -4;
         const double* Qin = qbuf[(l + 1) & 1];
         double* Qout = qbuf[l & 1];
