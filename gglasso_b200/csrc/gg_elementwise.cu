@@ -385,36 +385,37 @@ __global__ void __launch_bounds__(256)
 prox_band_kernel(const double* __restrict__ V, double* __restrict__ Theta, const double* __restrict__ ctrl,
                  double lambda1, double lambda2, int K, int nb, int p, int row0)
 {
-    extern __shared__ double ysm[];              // K * 256
+    extern __shared__ double ysm[];              // K * blockDim.x  (block size shrinks for large K)
     if (ctrl[GG_C_DONE] != 0.0) return;
     const double inv_rho = 1.0 / ctrl[GG_C_RHO];
     const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
+    const int T = blockDim.x;
     const size_t slab = (size_t)nb * p;
-    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t e = (size_t)blockIdx.x * T + threadIdx.x;
     if (e >= slab) return;
     const int r = (int)(e / p), c = (int)(e - (size_t)r * p);
     double* y = ysm + threadIdx.x;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) y[k * 256] = V[k * slab + e];
+    for (int k = 0; k < K; ++k) y[k * T] = V[k * slab + e];
     if (row0 + r != c) {
         if (REG == 0) {
             double ss = 0.0;
             for (int k = 0; k < K; ++k) {
-                const double u = gg_soft(y[k * 256], l1);
-                y[k * 256] = u;
+                const double u = gg_soft(y[k * T], l1);
+                y[k * T] = u;
                 ss += u * u;
             }
             const double nrm = sqrt(ss);
             const double a = nrm > l2 ? nrm : l2;
             const double f = a - l2;
-            for (int k = 0; k < K; ++k) y[k * 256] = (y[k * 256] * f) / a;
+            for (int k = 0; k < K; ++k) y[k * T] = (y[k * T] * f) / a;
         } else {
-            gg_tv1d_inplace(y, K, 256, l2);
-            for (int k = 0; k < K; ++k) y[k * 256] = gg_soft(y[k * 256], l1);
+            gg_tv1d_inplace(y, K, T, l2);
+            for (int k = 0; k < K; ++k) y[k * T] = gg_soft(y[k * T], l1);
         }
     }
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) Theta[k * slab + e] = y[k * 256];
+    for (int k = 0; k < K; ++k) Theta[k * slab + e] = y[k * T];
 }
 
 // ==========================================================================================
@@ -548,17 +549,21 @@ int gg_launch_add3(const double* Omega, const double* L, const double* X, double
 int gg_launch_prox_band(const double* V, double* Theta, const double* ctrl, double l1, double l2, int reg, int K,
                         int nb, int p, int row0, cudaStream_t st)
 {
-    const size_t smem = (size_t)K * 256 * sizeof(double);
+    // the K-vector of every entry lives in shared memory: shrink the block until K*T*8 fits (~96 KB keeps two
+    // CTAs per SM); K up to ~3000 is supported with 32-thread blocks
+    int T = 256;
+    while (T > 32 && (size_t)K * T * sizeof(double) > 96 * 1024) T >>= 1;
+    const size_t smem = (size_t)K * T * sizeof(double);
     if (smem > 200 * 1024) return -2;
     const size_t slab = (size_t)nb * p;
-    const unsigned grid = (unsigned)((slab + 255) / 256);
+    const unsigned grid = (unsigned)((slab + T - 1) / T);
     if (grid == 0) return 0;
     if (reg == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        prox_band_kernel<0><<<grid, 256, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
+        prox_band_kernel<0><<<grid, T, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        prox_band_kernel<1><<<grid, 256, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
+        prox_band_kernel<1><<<grid, T, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
     }
     GG_CHECK_LAUNCH();
     return 0;

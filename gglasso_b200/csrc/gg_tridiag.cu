@@ -385,9 +385,10 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
                 if (rho * fabs(sz[nj]) <= tol) { df[ndf++] = nj; continue; }
                 if (pj < 0) { pj = nj; continue; }
                 double s = sz[pj], c = sz[nj];
-                const double tau = hypot(c, s);
+                const double tau = sqrt(c * c + s * s);          // |z| <= 1 after normalisation: no overflow
+                const double itau = 1.0 / tau;
                 const double tt = sd[nj] - sd[pj];
-                c /= tau; s = -s / tau;
+                c *= itau; s = -s * itau;
                 if (fabs(tt * c * s) <= tol) {
                     sz[nj] = tau; sz[pj] = 0.0;
                     rp[nrot] = pj; rn[nrot] = nj; rc[nrot] = c; rs[nrot] = s; ++nrot;
@@ -542,10 +543,20 @@ dc_zhat_kernel(int n, int level, DcWs ws, const int* __restrict__ skip)
     const double* dl = ws.dl + (size_t)m * n + lo;
     const double* Dm = ws.U + (size_t)m * n * n + (size_t)lo * n + lo;
     const double di = dl[i];
-    double prod = Dm[(size_t)i * n + i];
-    for (int j = 0; j < k; ++j) {
-        if (j != i) prod *= Dm[(size_t)j * n + i] / (di - dl[j]);
+    // four independent partial products: the FP64 divisions are latency bound, not throughput bound
+    double pr[4] = {Dm[(size_t)i * n + i], 1.0, 1.0, 1.0};
+    int j = 0;
+    for (; j + 4 <= k; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j + u;
+            const double num = Dm[(size_t)jj * n + i], den = di - dl[jj];
+            pr[u] *= (jj != i) ? num / den : 1.0;
+        }
     }
+    for (; j < k; ++j)
+        if (j != i) pr[0] *= Dm[(size_t)j * n + i] / (di - dl[j]);
+    const double prod = (pr[0] * pr[1]) * (pr[2] * pr[3]);
     ws.zhat[(size_t)m * n + lo + i] = copysign(sqrt(-prod), ws.wnd[(size_t)m * n + lo + i]);
 }
 
@@ -707,7 +718,7 @@ bt_larft_kernel(const double* __restrict__ Vh, const double* __restrict__ tau, i
 // Each CTA owns BT_R rows of Q (row-major, n columns) and applies all panels, last to first:
 //   Y = Band V_b ; Y <- Y T_b^T ; Band <- Band - Y V_b^T
 #define BT_KC 32
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 bt_apply_kernel(double* __restrict__ Q, const double* __restrict__ Vh, const double* __restrict__ Tm, int n,
                 int npanels, const int* __restrict__ skip)
 {
@@ -732,16 +743,34 @@ bt_apply_kernel(double* __restrict__ Q, const double* __restrict__ Vh, const dou
         const double* Tg = Tm + ((size_t)m * npanels + pb) * BT_NB * BT_NB;
         for (int idx = tid; idx < BT_NB * BT_NB; idx += 256) Tsm[idx / BT_NB][idx % BT_NB] = Tg[idx];
         // ---- Y = Band V_b ------------------------------------------------------------------
+        // software pipeline: the next 32x32 band / panel tiles are fetched into registers while the
+        // current ones (in shared memory) feed the tensor cores
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        for (int i0 = istart; i0 < n; i0 += BT_KC) {
-            for (int idx = tid; idx < BT_R * BT_KC; idx += 256) {
+        double pb_[4], pv_[4];
+        auto fetch = [&](int i0, bool band) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + 256 * q;
                 const int r = idx / BT_KC, ii = idx % BT_KC;
-                const int gr = r0 + r, gi = i0 + ii;
-                Bt[r][ii] = (gr < n && gi < n) ? Qm[(size_t)gr * n + gi] : 0.0;
-                const int gj = j0 + r;                      // BT_R == BT_NB
-                Vt_[r][ii] = (gj < n - 1 && gi < n) ? V[(size_t)gj * n + gi] : 0.0;
+                const int gi = i0 + ii, gj = j0 + r, gr = r0 + r;
+                pv_[q] = (gj < n - 1 && gi < n) ? V[(size_t)gj * n + gi] : 0.0;
+                if (band) pb_[q] = (gr < n && gi < n) ? Qm[(size_t)gr * n + gi] : 0.0;
             }
+        };
+        auto stash = [&](bool band) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + 256 * q;
+                const int r = idx / BT_KC, ii = idx % BT_KC;
+                Vt_[r][ii] = pv_[q];
+                if (band) Bt[r][ii] = pb_[q];
+            }
+        };
+        fetch(istart, true);
+        for (int i0 = istart; i0 < n; i0 += BT_KC) {
+            stash(true);
             __syncthreads();
+            if (i0 + BT_KC < n) fetch(i0 + BT_KC, true);
 #pragma unroll
             for (int k0 = 0; k0 < BT_KC; k0 += 4) {
                 const double fa = Bt[tr * 8 + fr][k0 + fc];
@@ -768,13 +797,11 @@ bt_apply_kernel(double* __restrict__ Q, const double* __restrict__ Vh, const dou
         }
         __syncthreads();
         // ---- Band -= Y2 V_b^T -------------------------------------------------------------------
+        fetch(istart, false);
         for (int i0 = istart; i0 < n; i0 += BT_KC) {
-            for (int idx = tid; idx < BT_NB * BT_KC; idx += 256) {
-                const int jj = idx / BT_KC, ii = idx % BT_KC;
-                const int gj = j0 + jj, gi = i0 + ii;
-                Vt_[jj][ii] = (gj < n - 1 && gi < n) ? V[(size_t)gj * n + gi] : 0.0;
-            }
+            stash(false);
             __syncthreads();
+            if (i0 + BT_KC < n) fetch(i0 + BT_KC, false);
             // output tile: BT_R x BT_KC = 4 x 4 tiles of 8x8; warp -> row tile tr, col tiles tc0 + {0,1}
             double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll

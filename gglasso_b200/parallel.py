@@ -37,9 +37,11 @@ class KShard:
     """layout bookkeeping for a K-sharded (K_total, p, p) stack."""
 
     def __init__(self, K_total, p, group=None):
-        self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # group=False forces a single-rank layout even inside an initialised process group
+        local = group is False or not dist.is_initialized()
+        self.group = None if local else group
+        self.world = 1 if local else dist.get_world_size(group)
+        self.rank = 0 if local else dist.get_rank(group)
         self.K_total, self.p = K_total, p
         self.kparts = partition(K_total, self.world)
         self.rparts = partition(p, self.world)
@@ -111,7 +113,7 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
     from ._lib import C_DONE, C_ITER, NPART
     assert reg in ['GGL', 'FGL'] and min(lambda1, lambda2) > 0 and rho > 0
     K_loc, p, _ = S_local.shape
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    world = 1 if (group is False or not dist.is_initialized()) else dist.get_world_size(group)
     if K_total is None:
         t = torch.tensor([K_loc], dtype=torch.int64, device="cuda")
         if world > 1:
@@ -119,7 +121,7 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
         K_total = int(t.item())
     sh = KShard(K_total, p, group)
     assert sh.K_loc == K_loc, "each rank must hold partition(K_total, world)[rank] instances"
-    nk = None if n_samples is None else float(n_samples) * np.ones(K_loc)
+    nk = None if n_samples is None else np.asarray(n_samples, dtype=np.float64) * np.ones(K_loc)
     mu = None
     if latent:
         mu = (mu1_local * np.ones(K_loc)) if np.isscalar(mu1_local) else np.asarray(mu1_local, dtype=np.float64)

@@ -449,3 +449,39 @@ def test_block_sgl_with_mask_and_warm_start_arrays():
     ref = orc.block_sgl(S, 0.1, Om0, Theta_0=np.eye(p), X_0=X0, tol=1e-8, rtol=1e-8, lambda1_mask=mask)
     for k in ("Theta", "Omega", "X"):
         assert np.linalg.norm(sol[k] - ref[k]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(ref[k])), k
+
+
+@pytest.mark.parametrize("reg", ["GGL", "FGL"])
+def test_admm_mgl_large_K_uses_band_prox(reg):
+    """K beyond the tile-pair kernel's shared-memory budget (K > 90) goes through the row-band prox."""
+    from gglasso_b200 import ADMM_MGL
+    from oracle import admm_oracle as orc
+    rng = np.random.default_rng(9)
+    K, p, N = 130, 12, 60
+    S = np.stack([np.cov(rng.standard_normal((p, N)), bias=True) for _ in range(K)])
+    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    (sol, info), out = _quiet(ADMM_MGL, S, 0.1, 0.05, reg, Om0, tol=1e-7, rtol=1e-7)
+    ref, rinfo = orc.admm_mgl(S, 0.1, 0.05, reg, Om0, tol=1e-7, rtol=1e-7)
+    assert info["status"] == rinfo["status"] and f"after {rinfo['iterations']} iterations" in out
+    for k in ("Omega", "Theta", "X"):
+        assert _rel(sol[k], ref[k]) < PER_ITER_TOL, k
+    assert np.array_equal(sol["Theta"] != 0, ref["Theta"] != 0)
+
+
+def test_grid_search_on_device_solver_matches_oracle_solver():
+    """lambda grid driver (grid_search_dist, single rank) with the B200 solver vs the same driver with the CPU oracle."""
+    from gglasso_b200 import ADMM_MGL
+    from gglasso_b200.parallel import grid_search_dist
+    from oracle import admm_oracle as orc
+    rng = np.random.default_rng(3)
+    K, p, N = 3, 30, 150
+    S = np.stack([np.cov(rng.standard_normal((p, N)), bias=True) for _ in range(K)])
+    l1, l2 = np.logspace(-0.5, -1.5, 3), np.logspace(-1, -2, 2)
+
+    def cpu_solver(S, a, b, reg, Om0, tol=1e-7, rtol=1e-7, **kw):
+        return orc.admm_mgl(S, a, b, reg, Om0, tol=tol, rtol=rtol)
+    (sc_g, ix_g, best_g), _ = _quiet(grid_search_dist, ADMM_MGL, S, np.full(K, N), "GGL", l1, l2, gamma=0.1)
+    sc_c, ix_c, best_c = grid_search_dist(cpu_solver, S, np.full(K, N), "GGL", l1, l2, gamma=0.1)
+    np.testing.assert_allclose(sc_g, sc_c, rtol=1e-8)
+    assert tuple(ix_g) == tuple(ix_c)
+    assert _rel(best_g["Theta"], best_c["Theta"]) < PER_ITER_TOL
