@@ -81,25 +81,40 @@ prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
     const size_t base = (size_t)m * pp;
     const size_t stride = (size_t)gridDim.x * EW_THREADS;
     double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += stride) {
-        const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
-        const double om = Omega[base + e];
-        const double x = X[base + e];
-        const double l = L ? L[base + e] : 0.0;
-        double a = om;
-        if (L) a = a + l;
-        a = a + x;
-        const double thr = inv_rho * (lam_mat ? lam_mat[base + e] : lam);
-        const double th = (i == j) ? a : gg_soft(a, thr);
-        Theta[base + e] = th;
-        if (C) {
-            C[base + e] = (th - x) - om;          // C_t = Theta_t - X_t - Omega_t
-        } else {
-            const double xn = (x + om) - th;      // X_t + Omega_t - Theta_t (+ L_t = 0)
-            X[base + e] = xn;
-            if (i < pb && j < pb) {
-                const double d1 = om - th, d2 = om - Omega_prev[base + e];
-                acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+    for (size_t e0 = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e0 < pp; e0 += stride * EW_UNROLL) {
+        double vom[EW_UNROLL], vx[EW_UNROLL], vl[EW_UNROLL], vp[EW_UNROLL], vlam[EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {               // all loads of the batch first (memory-level parallelism)
+            const size_t e = e0 + u * stride;
+            if (e < pp) {
+                vom[u] = Omega[base + e];
+                vx[u] = X[base + e];
+                vl[u] = L ? L[base + e] : 0.0;
+                vp[u] = C ? 0.0 : Omega_prev[base + e];
+                vlam[u] = lam_mat ? lam_mat[base + e] : lam;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            const size_t e = e0 + u * stride;
+            if (e >= pp) continue;
+            const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
+            const double om = vom[u], x = vx[u], l = vl[u];
+            double a = om;
+            if (L) a = a + l;
+            a = a + x;
+            const double thr = inv_rho * vlam[u];
+            const double th = (i == j) ? a : gg_soft(a, thr);
+            Theta[base + e] = th;
+            if (C) {
+                C[base + e] = (th - x) - om;          // C_t = Theta_t - X_t - Omega_t
+            } else {
+                const double xn = (x + om) - th;      // X_t + Omega_t - Theta_t (+ L_t = 0)
+                X[base + e] = xn;
+                if (i < pb && j < pb) {
+                    const double d1 = om - th, d2 = om - vp[u];
+                    acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+                }
             }
         }
     }
@@ -127,14 +142,27 @@ dual_update_kernel(double* __restrict__ X, const double* __restrict__ Omega, con
     const size_t base = (size_t)m * pp;
     const size_t stride = (size_t)gridDim.x * EW_THREADS;
     double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += stride) {
-        const double om = Omega[base + e], th = Theta[base + e], x = X[base + e];
-        const double l = L ? L[base + e] : 0.0;
-        const double res = L ? ((om - th) + l) : (om - th);       // Omega - Theta + L
-        const double xn = sgl_order ? (L ? (((x + om) - th) + l) : ((x + om) - th)) : (x + res);
-        X[base + e] = xn;
-        const double tl = th - l, d2 = om - Omega_prev[base + e];
-        acc[0] += om * om; acc[1] += tl * tl; acc[2] += xn * xn; acc[3] += res * res; acc[4] += d2 * d2;
+    for (size_t e0 = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e0 < pp; e0 += stride * EW_UNROLL) {
+        double vom[EW_UNROLL], vth[EW_UNROLL], vx[EW_UNROLL], vl[EW_UNROLL], vp[EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            const size_t e = e0 + u * stride;
+            if (e < pp) {
+                vom[u] = Omega[base + e]; vth[u] = Theta[base + e]; vx[u] = X[base + e];
+                vl[u] = L ? L[base + e] : 0.0; vp[u] = Omega_prev[base + e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            const size_t e = e0 + u * stride;
+            if (e >= pp) continue;
+            const double om = vom[u], th = vth[u], x = vx[u], l = vl[u];
+            const double res = L ? ((om - th) + l) : (om - th);       // Omega - Theta + L
+            const double xn = sgl_order ? (L ? (((x + om) - th) + l) : ((x + om) - th)) : (x + res);
+            X[base + e] = xn;
+            const double tl = th - l, d2 = om - vp[u];
+            acc[0] += om * om; acc[1] += tl * tl; acc[2] += xn * xn; acc[3] += res * res; acc[4] += d2 * d2;
+        }
     }
     gg_block_sum<GG_NPART>(acc, scratch);
     if (threadIdx.x == 0) {
@@ -178,7 +206,7 @@ prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
     // ---- phase A: gather the K-vector of (Omega + L) + X, prox in place --------------------
     if (upper) {
         const size_t e = (size_t)i * p + j;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 0; k < K; ++k) {
             double v = Omega[k * pp + e];
             if (LATENT) v = v + L[k * pp + e];
@@ -207,34 +235,50 @@ prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
     __syncthreads();
 
     // ---- phase B: write Theta (+C or X and partial sums) for tile (I,J) and its mirror ------
+    // Both sides are handled in the same k-loop so that six independent global loads are in flight per
+    // iteration (the kernel is latency bound on these re-reads: ncu long-scoreboard 46 %).
     double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-        int ii, jj, sl;
-        if (side == 0) {
-            ii = i; jj = j;
-            sl = (I < J || tr <= tc) ? slot : (tc * PLD + tr);
-        } else {
-            if (I == J) break;
-            ii = J * PT + tr; jj = I * PT + tc;     // element of tile (J,I)
-            sl = tc * PLD + tr;                     // = value of its transpose (jj, ii)
-        }
-        if (ii < p && jj < p) {
-            const size_t e = (size_t)ii * p + jj;
-#pragma unroll 2
+    {
+        const int sl0 = (I < J || tr <= tc) ? slot : (tc * PLD + tr);
+        const bool ok0 = valid;
+        const size_t e0 = (size_t)i * p + j;
+        const int i1 = J * PT + tr, j1 = I * PT + tc;          // element of the mirror tile (J,I)
+        const bool ok1 = (I < J) && (i1 < p) && (j1 < p);
+        const size_t e1 = (size_t)i1 * p + j1;
+        const int sl1 = tc * PLD + tr;                         // = value of its transpose (j1, i1)
+        if (ok0 || ok1) {
+            const size_t ea = ok0 ? e0 : e1, eb = ok1 ? e1 : e0;   // keep addresses valid when one side is off
+#pragma unroll (LATENT ? 4 : 2)
             for (int k = 0; k < K; ++k) {
-                const double th = ysm[k * PSLOT + sl];
-                const double om = Omega[k * pp + e];
-                const double x = X[k * pp + e];
-                Theta[k * pp + e] = th;
-                if (LATENT) {
-                    C[k * pp + e] = (th - x) - om;
-                } else {
-                    const double d1 = om - th;
-                    const double xn = x + d1;                  // X += Omega - Theta (+ L = 0)
-                    X[k * pp + e] = xn;
-                    const double d2 = om - Omega_prev[k * pp + e];
-                    acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+                const size_t o = (size_t)k * pp;
+                const double om0 = Omega[o + ea], x0 = X[o + ea];
+                const double om1 = Omega[o + eb], x1 = X[o + eb];
+                double p0 = 0.0, p1 = 0.0;
+                if (!LATENT) { p0 = Omega_prev[o + ea]; p1 = Omega_prev[o + eb]; }
+                const double th0 = ysm[k * PSLOT + sl0], th1 = ysm[k * PSLOT + sl1];
+                if (ok0) {
+                    Theta[o + e0] = th0;
+                    if (LATENT) {
+                        C[o + e0] = (th0 - x0) - om0;
+                    } else {
+                        const double d1 = om0 - th0;
+                        const double xn = x0 + d1;             // X += Omega - Theta (+ L = 0)
+                        X[o + e0] = xn;
+                        const double d2 = om0 - p0;
+                        acc[0] += om0 * om0; acc[1] += th0 * th0; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+                    }
+                }
+                if (ok1) {
+                    Theta[o + e1] = th1;
+                    if (LATENT) {
+                        C[o + e1] = (th1 - x1) - om1;
+                    } else {
+                        const double d1 = om1 - th1;
+                        const double xn = x1 + d1;
+                        X[o + e1] = xn;
+                        const double d2 = om1 - p1;
+                        acc[0] += om1 * om1; acc[1] += th1 * th1; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+                    }
                 }
             }
         }
