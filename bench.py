@@ -85,9 +85,15 @@ class ClockSampler:
 
 
 def cpu_reference_rate(S, cfg, iters):
-    """oracle port (CPU): iterations/sec for `iters` iterations of the same workload."""
+    """oracle port (CPU): iterations/sec for `iters` iterations of the same workload, all host threads
+    (torchrun exports OMP_NUM_THREADS=1; the BLAS pool is widened explicitly)."""
     from oracle import admm_oracle as orc
     orc.build_c()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     K, p = cfg["K"], cfg["p"]
     Om0 = np.repeat(np.eye(p)[None], K, 0)
     small = np.repeat(np.eye(8)[None], 2, 0)
