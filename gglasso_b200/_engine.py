@@ -229,7 +229,7 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
 
     Returns (state, info) where info carries iteration counts, status and histories (numpy).
     """
-    S3 = S if S.ndim == 3 else S[None]
+    S3 = S if S.ndim == 3 else S[None]       # numpy arrays or device tensors
     M, p, _ = S3.shape
     mpp = M if kind == "mgl" else 1
     st = AdmmState(S3, Omega_0.reshape(S3.shape), None if Theta_0 is None else Theta_0.reshape(S3.shape),

@@ -241,6 +241,79 @@ def grid_search_dist(solver, S, N, reg, l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7, 
     return scores, best_ix, best
 
 
+def _score_device(st, Omega_unused, N, gamma, method):
+    """eBIC / AIC of the current Theta on the device (reference: src/gglasso/helper/model_selection.py:813-869,
+    robust_logdet :884-894).  Eigenvalues come from the CUDA eigensolver (values only); the remaining terms are
+    reductions over arrays that are already resident."""
+    K, p = st.M, st.p
+    Theta = st.Theta
+    D = st.eig.eigh(Theta.clone(), ctrl=None, mpp=1, vectors=0, stream=st.stream)          # (K,p)
+    dmin = D.min(dim=1).values
+    logdet = torch.where(dmin > 1e-12, torch.log(D.clamp_min(1e-300)).sum(1), torch.full_like(dmin, -float("inf")))
+    inner = (st.S * Theta).sum((1, 2))
+    E = (torch.count_nonzero(Theta.reshape(K, -1), dim=1).to(torch.float64) - p) / 2
+    Nd = torch.as_tensor(np.asarray(N, dtype=np.float64), device=st.dev)
+    pen = E * (torch.log(Nd) + 4 * np.log(p) * gamma) if method == "eBIC" else E
+    return float((Nd * (inner - logdet) + pen).sum().item())
+
+
+def grid_search_device(S, N, reg, l1, l2, method="eBIC", gamma=0.1, tol=1e-7, rtol=1e-7, latent=False, mu1=None,
+                       group=None):
+    """lambda1 x lambda2 grid with everything resident on the GPU: S is uploaded once, each grid point runs the
+    device ADMM loop, is scored on the device (eBIC/AIC) and hands its Omega to the next point of the column as
+    warm start without touching the host; only the winning solution is copied back.  Columns (lambda1 values) are
+    dealt round-robin to the ranks of ``group`` (one process per GPU); see grid_search_dist for the semantics.
+
+    Returns (scores (len(l2), len(l1)), iterations (same shape), best_index (g1, g2), best_sol) on every rank.
+    """
+    from ._engine import run_admm, to_host, require_cuda, to_dev
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    assert method in ("eBIC", "AIC") and reg in ("GGL", "FGL")
+    K, p, _ = S.shape
+    dev = require_cuda()
+    S_dev = to_dev(S, dev)
+    l1 = np.asarray(l1, dtype=float)
+    l2 = np.asarray(l2, dtype=float)
+    scores = np.full((len(l2), len(l1)), np.nan)
+    iters = np.zeros((len(l2), len(l1)), dtype=int)
+    eye = torch.eye(p, dtype=torch.float64, device=dev).repeat(K, 1, 1)
+    best, best_score, best_ix = None, np.inf, None
+    mu = None
+    if latent:
+        mu = mu1 * np.ones(K) if np.isscalar(mu1) else np.asarray(mu1, dtype=np.float64)
+    for g2 in range(rank, len(l1), world):
+        Omega_0 = eye
+        for g1 in range(len(l2)):
+            st, res = run_admm("mgl", S_dev, Omega_0, None, None, lambda1=float(l1[g2]), lambda2=float(l2[g1]),
+                               reg=reg, tol=tol, rtol=rtol, latent=latent, mu=mu)
+            n = int(res["iters"][0])
+            Omega_0 = st.final_omega(res["iters"])
+            sc = _score_device(st, Omega_0, N, gamma, method)
+            scores[g1, g2], iters[g1, g2] = sc, n
+            if sc < best_score:
+                best_score, best_ix = sc, (g1, g2)
+                best = {"Omega": Omega_0.clone(), "Theta": st.Theta.clone(), "X": st.X.clone(),
+                        "L": st.L.clone() if latent else None}
+    if best is not None:
+        best = {k: (to_host(v) if v is not None else np.zeros((K, p, p))) for k, v in best.items()}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (scores, iters, best_score, best_ix), group=group)
+        scores = np.full_like(scores, np.nan)
+        owner, owner_score = 0, np.inf
+        for r, (sc, itr, bs, bix) in enumerate(gathered):
+            m = ~np.isnan(sc)
+            scores[m] = sc[m]
+            iters[m] = itr[m]
+            if bs < owner_score:
+                owner, owner_score, best_ix = r, bs, bix
+        obj = [best if rank == owner else None]
+        dist.broadcast_object_list(obj, src=owner, group=group)
+        best = obj[0]
+    return scores, iters, best_ix, best
+
+
 def assign_blocks(sizes, world):
     """longest-processing-time assignment of connected components (cost ~ size^3) to ranks."""
     order = np.argsort(-np.asarray(sizes, dtype=float) ** 3, kind="stable")

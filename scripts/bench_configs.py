@@ -4,7 +4,7 @@ import contextlib, io, json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gglasso_b200 import ADMM_MGL, ADMM_SGL, block_SGL, get_connected_components
-from gglasso_b200.parallel import grid_search_dist
+from gglasso_b200.parallel import grid_search_dist, grid_search_device
 from gglasso_b200.datagen import synthetic_mgl, synthetic_sgl
 from oracle import admm_oracle as orc
 skip_cpu = "--skip-cpu" in sys.argv
@@ -60,6 +60,9 @@ S = synthetic_mgl(10, 500, N=1000, seed=1234); N = np.full(10, 1000)
 l1 = np.logspace(0, -3, 10); l2 = np.logspace(-1, -4, 10)
 t, (scores, ix, best) = wall(lambda: grid_search_dist(ADMM_MGL, S, N, "GGL", l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7))
 d = dict(gpu_grid_s=t, best_ix=[int(ix[0]), int(ix[1])], best_lambda=[float(l1[ix[1]]), float(l2[ix[0]])], nan_scores=int(np.isnan(scores).sum()))
+td, (sc_dev, it_dev, ix_dev, _) = wall(lambda: grid_search_device(S, N, "GGL", l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7))
+d.update(gpu_grid_device_resident_s=td, device_best_ix=[int(ix_dev[0]), int(ix_dev[1])], total_admm_iterations=int(it_dev.sum()),
+         device_vs_host_scores_rel=float(np.nanmax(np.abs(sc_dev - scores) / np.abs(scores))))
 if not skip_cpu:
     def cpu_solver(S, a, b, reg, Om0, tol=1e-7, rtol=1e-7, **kw): return orc.admm_mgl(S, a, b, reg, Om0, tol=tol, rtol=rtol)
     j = 4   # one representative column (lambda1 = l1[4])

@@ -485,3 +485,21 @@ def test_grid_search_on_device_solver_matches_oracle_solver():
     np.testing.assert_allclose(sc_g, sc_c, rtol=1e-8)
     assert tuple(ix_g) == tuple(ix_c)
     assert _rel(best_g["Theta"], best_c["Theta"]) < PER_ITER_TOL
+
+
+def test_grid_search_device_resident_matches_host_driver():
+    """device-resident grid (scores on the GPU, warm starts never leave the device) vs the host-scored driver."""
+    from gglasso_b200 import ADMM_MGL
+    from gglasso_b200.parallel import grid_search_device, grid_search_dist
+    rng = np.random.default_rng(3)
+    K, p, N = 3, 30, 150
+    S = np.stack([np.cov(rng.standard_normal((p, N)), bias=True) for _ in range(K)])
+    l1, l2 = np.logspace(-0.5, -1.5, 3), np.logspace(-1, -2, 2)
+    sc_d, it_d, ix_d, best_d = grid_search_device(S, np.full(K, N), "GGL", l1, l2, gamma=0.1)
+    (sc_h, ix_h, best_h), _ = _quiet(grid_search_dist, ADMM_MGL, S, np.full(K, N), "GGL", l1, l2, gamma=0.1)
+    np.testing.assert_allclose(sc_d, sc_h, rtol=1e-9)
+    assert tuple(ix_d) == tuple(ix_h) and it_d.min() >= 1
+    for k in ("Omega", "Theta", "X"):
+        assert _rel(best_d[k], best_h[k]) < PER_ITER_TOL, k
+    sc_a, _, _, _ = grid_search_device(S, np.full(K, N), "FGL", l1[:1], l2[:1], method="AIC")
+    assert np.isfinite(sc_a).all()
