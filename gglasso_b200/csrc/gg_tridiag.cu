@@ -198,6 +198,115 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restr
     }
 }
 
+// Tail of the tridiagonalisation: once the trailing block has at most TR_TAIL rows it fits in shared memory, and
+// one CTA per matrix finishes all remaining columns in a single launch (block barriers instead of ~2*TR_TAIL
+// dependent kernel launches).  Takes over at column js: finishes w_{js-1} from the accumulated y, loads the
+// upper triangle of the trailing block with the pending rank-2 update applied (mirrored into a full symmetric
+// tile), then runs the unblocked Householder steps in place.
+#define TR_TAIL 144
+__global__ void __launch_bounds__(512)
+tr_tail_kernel(const double* __restrict__ A, int n, int js, TrWs ws, const int* __restrict__ skip)
+{
+    extern __shared__ double tsm[];
+    const int m = blockIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (skip && skip[m]) return;
+    const int ts = n - js, ld = ts | 1;
+    double* B = tsm;                      // ts x ld
+    double* vv = tsm + (size_t)ts * ld;   // ts
+    double* ww = vv + ts;                 // ts
+    double* yy = ww + ts;                 // ts
+    double* red = yy + ts;                // 64
+    double* bc = red + 64;                // 4
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double* Am = A + (size_t)m * n * n;
+    double* tau = ws.tau + (size_t)m * n;
+    double* dd = ws.d + (size_t)m * n;
+    double* ee = ws.e + (size_t)m * n;
+    double* Vh = ws.Vh + (size_t)m * n * n;
+    const bool pend = js >= 1;
+    if (pend) {
+        const double* y = ws.y + (size_t)m * n;
+        const double* vprev = ws.vbuf + ((size_t)m * 2 + ((js + 1) & 1)) * n;
+        const double tp = tau[js - 1];
+        double part[1] = {0.0};
+        for (int r = tid; r < ts; r += nt) part[0] += (tp * y[js + r]) * vprev[js + r];
+        gg_block_sum<1>(part, red);
+        if (tid == 0) bc[0] = -0.5 * tp * part[0];
+        __syncthreads();
+        const double alpha = bc[0];
+        for (int r = tid; r < ts; r += nt) {
+            vv[r] = vprev[js + r];
+            ww[r] = tp * y[js + r] + alpha * vprev[js + r];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < ts * ts; idx += nt) {
+        const int r = idx / ts, c = idx - r * ts;
+        const int rr = r < c ? r : c, cc = r < c ? c : r;
+        double a = Am[(size_t)(js + rr) * n + js + cc];
+        if (pend) a = a - vv[rr] * ww[cc] - ww[rr] * vv[cc];
+        B[r * ld + c] = a;
+    }
+    __syncthreads();
+    for (int jj = 0; jj < ts; ++jj) {
+        const int j = js + jj, len = ts - jj - 1;
+        if (tid == 0) dd[j] = B[jj * ld + jj];
+        if (len == 0) break;
+        const double* x = B + (size_t)jj * ld + jj + 1;          // row jj to the right of the diagonal
+        double part[1] = {0.0};
+        for (int i = 1 + tid; i < len; i += nt) part[0] += x[i] * x[i];
+        gg_block_sum<1>(part, red);
+        if (tid == 0) {
+            const double alpha = x[0], xn2 = part[0];
+            double t = 0.0, beta = alpha, scale = 0.0;
+            if (xn2 > 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                t = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            tau[j] = t; ee[j] = beta; bc[1] = scale; bc[2] = t;
+        }
+        __syncthreads();
+        const double scale = bc[1], tj = bc[2];
+        for (int i = tid; i < len; i += nt) {
+            const double v = (i == 0) ? 1.0 : x[i] * scale;
+            vv[i] = v;
+            Vh[(size_t)j * n + j + 1 + i] = v;
+        }
+        __syncthreads();
+        // y = B22 v  (two threads per row, even / odd columns)
+        {
+            const int r = tid >> 1, h = tid & 1;
+            double s = 0.0;
+            if (r < len) {
+                const double* row = B + (size_t)(jj + 1 + r) * ld + jj + 1;
+                for (int c = h; c < len; c += 2) s = fma(row[c], vv[c], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (r < len && h == 0) yy[r] = s;
+        }
+        __syncthreads();
+        double dp[1] = {0.0};
+        for (int i = tid; i < len; i += nt) dp[0] += (tj * yy[i]) * vv[i];
+        gg_block_sum<1>(dp, red);
+        if (tid == 0) bc[3] = -0.5 * tj * dp[0];
+        __syncthreads();
+        const double al = bc[3];
+        for (int i = tid; i < len; i += nt) ww[i] = tj * yy[i] + al * vv[i];
+        __syncthreads();
+        {
+            const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+            for (int r = wid; r < len; r += nw) {
+                double* row = B + (size_t)(jj + 1 + r) * ld + jj + 1;
+                const double vr = vv[r], wr = ww[r];
+                for (int c = lane; c < len; c += 32) row[c] -= vr * ww[c] + wr * vv[c];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // =============================================================================================
 // stage 2: divide & conquer on the tridiagonal matrices
 // =============================================================================================
@@ -941,7 +1050,8 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         cfg.stream = s;
         cfg.attrs = pdl;
         cfg.numAttrs = 1;
-        for (int j = 0; j < n; ++j) {
+        const int js = (which == 1 || which == 2) ? n : (n > TR_TAIL ? n - TR_TAIL : 0);   // tail takes over at column js
+        for (int j = 0; j < js; ++j) {
             if (which != 2) {
                 cfg.gridDim = dim3(M); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0;
                 cudaError_t e = cudaLaunchKernelEx(&cfg, tr_col_kernel, A, n, j, tw, (const int*)skip);
@@ -954,6 +1064,19 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, tw, (const int*)skip, nt);
                 if (e != cudaSuccess) return (int)e;
             }
+        }
+        if (js < n) {
+            const int ts = n - js;
+            const size_t tsm = sizeof(double) * ((size_t)ts * (ts | 1) + 3 * ts + 64 + 4);
+            static bool tattr = false;
+            if (!tattr) {
+                cudaFuncSetAttribute(tr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * ((size_t)TR_TAIL * (TR_TAIL | 1) + 3 * TR_TAIL + 68)));
+                tattr = true;
+            }
+            cfg.gridDim = dim3(M); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = tsm;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip);
+            if (e != cudaSuccess) return (int)e;
         }
     }
     GG_CHECK_LAUNCH();
