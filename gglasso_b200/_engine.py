@@ -224,7 +224,7 @@ class AdmmState:
 def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None, lam_mat=None, rho=1.0,
              max_iter=1000, tol=1e-7, rtol=1e-4, stopping_criterion="boyd", update_rho=True, verbose=False,
              measure=False, latent=False, mu=None, nk=None, header=None, check_every=None, trace=None,
-             check_symmetric=False, pvec=None):
+             check_symmetric=False, pvec=None, Mblk=None, print_rho=False):
     """Run the device ADMM loop.  ``kind``: 'mgl' (one problem of K matrices) or 'sgl' (M problems).
 
     Returns (state, info) where info carries iteration counts, status and histories (numpy).
@@ -251,6 +251,9 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     nparts = nparts_dual if latent else nparts_fused
     partials = torch.zeros((nprob, max(nparts_fused, nparts_dual), NPART), dtype=torch.float64, device=st.dev)
 
+    blk_nrm = None
+    if Mblk is not None:
+        blk_nrm = torch.zeros((M, (p // Mblk) ** 2), dtype=torch.float64, device=st.dev)
     if check_every is None:
         check_every = 1 if (measure or verbose or p > 400) else 4
     runtime = np.zeros(max_iter)
@@ -262,7 +265,9 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
 
     if verbose and header:
         print(header)
-        if stopping_criterion == "boyd":
+        if stopping_criterion == "boyd" and print_rho:
+            print("%4s\t%10s\t%10s\t%10s\t%10s\t%10s" % ("iter", "r_t", "s_t", "eps_pri", "eps_dual", "rho"))
+        elif stopping_criterion == "boyd":
             print("%4s\t%10s\t%10s\t%10s\t%10s" % ("iter", "r_t", "s_t", "eps_pri", "eps_dual"))
         else:
             print("%4s\t%10s" % ("iter", "kkt residual"))
@@ -278,6 +283,10 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             _lib.check(lib.gg_prox_mgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
                                        _p(st.ctrl), lambda1, lambda2, regi, M, p, _p(partials), stream),
                        "gg_prox_mgl")
+        elif Mblk is not None:
+            _lib.check(lib.gg_prox_fsgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
+                                        _p(st.ctrl), float(lambda1), int(Mblk), M, p, _p(partials), _p(blk_nrm),
+                                        stream), "gg_prox_fsgl")
         else:
             _lib.check(lib.gg_prox_sgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
                                        _p(st.ctrl), float(lambda1), _p(st.lam_mat), M, p, _p(partials), _p(st.pvec),
@@ -304,9 +313,14 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             if (it + 1) % check_every == 0 or it + 1 == max_iter:
                 ctrl = st.read_ctrl()
                 if verbose and nprob == 1:
-                    h = st.hist[0, printed:int(ctrl[0, C_ITER])].cpu().numpy()
-                    for row in h:
-                        print("%4d\t%10.4g\t%10.4g\t%10.4g\t%10.4g" % (printed, row[0], row[1], row[2], row[3]))
+                    ndone = int(ctrl[0, C_ITER])
+                    h = st.hist[0, printed:ndone].cpu().numpy()
+                    for i, row in enumerate(h):
+                        if print_rho:      # functional SGL prints the rho chosen for the NEXT iteration
+                            rho_next = h[i + 1][4] if i + 1 < len(h) else ctrl[0, C_RHO]
+                            print("%4d\t%10.4g\t%10.4g\t%10.4g\t%10.4g\t%10.4g" % (printed, row[0], row[1], row[2], row[3], rho_next))
+                        else:
+                            print("%4d\t%10.4g\t%10.4g\t%10.4g\t%10.4g" % (printed, row[0], row[1], row[2], row[3]))
                         printed += 1
                 if np.all(ctrl[:, C_DONE] != 0):
                     break

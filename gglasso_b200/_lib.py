@@ -27,6 +27,7 @@ SIGNATURES = {
     "gg_recon": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gg_sgl_nparts": (_i, [_i, _i]),
     "gg_prox_sgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _i, _vp, _vp, _vp]),
+    "gg_prox_fsgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp, _vp]),
     "gg_mgl_ntile": (_i, [_i]),
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),

@@ -6,7 +6,7 @@
 int gg_launch_build_w(const double*, const double*, double*, const double*, const double*, const double*, int, int,
                       int, double*, cudaStream_t);
 int gg_launch_prox_sgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
-                       const double*, int, int, double*, const int*, cudaStream_t);
+                       const double*, int, int, double*, const int*, double*, int, cudaStream_t);
 int gg_launch_dual_update(double*, const double*, const double*, const double*, const double*, const double*, int,
                           int, int, int, double*, cudaStream_t);
 int gg_launch_prox_mgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
@@ -69,8 +69,17 @@ int gg_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, 
                 void* stream)
 {
     if (M <= 0 || p <= 0) return -1;
-    return gg_launch_prox_sgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, M, p, partials, pvec,
+    return gg_launch_prox_sgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, M, p, partials, pvec, nullptr, 0,
                               (cudaStream_t)stream);
+}
+
+int gg_prox_fsgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta, double* C,
+                 const double* ctrl, double lam, int Mblk, int M, int p, double* partials, double* blk_nrm,
+                 void* stream)
+{
+    if (M <= 0 || p <= 0 || Mblk <= 0 || p % Mblk != 0 || blk_nrm == nullptr) return -1;
+    return gg_launch_prox_sgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, nullptr, M, p, partials, nullptr, blk_nrm,
+                              Mblk, (cudaStream_t)stream);
 }
 
 int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta, double* C,

@@ -69,7 +69,7 @@ prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
                 const double* __restrict__ L, double* __restrict__ X, double* __restrict__ Theta,
                 double* __restrict__ C, const double* __restrict__ ctrl, double lam,
                 const double* __restrict__ lam_mat, int p, double* __restrict__ partials,
-                const int* __restrict__ pvec)
+                const int* __restrict__ pvec, const double* __restrict__ blk_nrm, int Mblk)
 {
     __shared__ double scratch[GG_NPART * 32];
     const int m = blockIdx.y;
@@ -104,7 +104,20 @@ prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
             if (L) a = a + l;
             a = a + x;
             const double thr = inv_rho * vlam[u];
-            const double th = (i == j) ? a : gg_soft(a, thr);
+            double th;
+            if (blk_nrm) {
+                // functional SGL (prox_sum_Frob, ggl_helper.py:45-66): off-diagonal MxM blocks are shrunk in
+                // Frobenius norm, v*(a-l)/a with a = max(|block|_F, l); diagonal blocks are kept
+                const int bi = i / Mblk, bj = j / Mblk, nbk = p / Mblk;
+                if (bi == bj) th = a;
+                else {
+                    const double nr = blk_nrm[(size_t)m * nbk * nbk + (size_t)(bi < bj ? bi : bj) * nbk + (bi < bj ? bj : bi)];
+                    const double aa = nr > thr ? nr : thr;
+                    th = (a * (aa - thr)) / aa;
+                }
+            } else {
+                th = (i == j) ? a : gg_soft(a, thr);
+            }
             Theta[base + e] = th;
             if (C) {
                 C[base + e] = (th - x) - om;          // C_t = Theta_t - X_t - Omega_t
@@ -126,6 +139,33 @@ prox_sgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
             for (int i = 0; i < GG_NPART; ++i) out[i] = acc[i];
         }
     }
+}
+
+// Frobenius norms of the strictly-upper MxM blocks of A = (Omega + L) + X  (functional SGL): one warp per block.
+__global__ void __launch_bounds__(256)
+fsgl_block_norm_kernel(const double* __restrict__ Omega, const double* __restrict__ L, const double* __restrict__ X,
+                       const double* __restrict__ ctrl, int p, int Mblk, double* __restrict__ blk_nrm)
+{
+    const int m = blockIdx.y;
+    if (ctrl[(size_t)m * GG_CTRL_STRIDE + GG_C_DONE] != 0.0) return;
+    const int nbk = p / Mblk;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pair = blockIdx.x * 8 + wid;
+    if (pair >= nbk * nbk) return;
+    const int bi = pair / nbk, bj = pair % nbk;
+    if (bi >= bj) return;
+    const size_t base = (size_t)m * p * p;
+    double ss = 0.0;
+    for (int e = lane; e < Mblk * Mblk; e += 32) {
+        const int r = e / Mblk, c = e % Mblk;
+        const size_t idx = base + (size_t)(bi * Mblk + r) * p + bj * Mblk + c;
+        double a = Omega[idx];
+        if (L) a = a + L[idx];
+        a = a + X[idx];
+        ss += a * a;
+    }
+    ss = gg_warp_sum(ss);
+    if (lane == 0) blk_nrm[(size_t)m * nbk * nbk + (size_t)bi * nbk + bj] = sqrt(ss);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -489,11 +529,17 @@ extern "C" int gg_sgl_nparts(int p, int M) { return ew_blocks((size_t)p * p, M);
 
 int gg_launch_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
                        double* C, const double* ctrl, double lam, const double* lam_mat, int M, int p,
-                       double* partials, const int* pvec, cudaStream_t st)
+                       double* partials, const int* pvec, double* blk_nrm, int Mblk, cudaStream_t st)
 {
     dim3 grid(gg_sgl_nparts(p, M), M);
+    if (blk_nrm) {
+        if (Mblk <= 0 || p % Mblk != 0) return -1;
+        const int nbk = p / Mblk;
+        dim3 gn((nbk * nbk + 7) / 8, M);
+        fsgl_block_norm_kernel<<<gn, 256, 0, st>>>(Omega, L, X, ctrl, p, Mblk, blk_nrm);
+    }
     prox_sgl_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, p, partials,
-                                                 pvec);
+                                                 pvec, blk_nrm, Mblk);
     GG_CHECK_LAUNCH();
     return 0;
 }

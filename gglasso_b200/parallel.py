@@ -314,6 +314,39 @@ def grid_search_device(S, N, reg, l1, l2, method="eBIC", gamma=0.1, tol=1e-7, rt
     return scores, iters, best_ix, best
 
 
+def block_SGL_dist(S, lambda1, Omega_0, Theta_0=None, X_0=None, rho=1., max_iter=1000, tol=1e-7, rtol=1e-3,
+                   stopping_criterion="boyd", update_rho=True, lambda1_mask=None, group=None, solver=None):
+    """block_SGL (src/gglasso/solver/single_admm_solver.py:326-475) with the connected components distributed over
+    the ranks: every rank computes the same components and the same LPT assignment (cost ~ size^3), solves its
+    share (small blocks as ragged batches on its GPU), and the disjoint block results are combined with one
+    all-reduce(sum) per output array.  ``solver`` (default: the B200 ADMM_SGL) is injectable for CPU tests."""
+    from .solver.single_admm_solver import _solve_components, get_connected_components
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    p = S.shape[0]
+    mask = np.ones((p, p)) if lambda1_mask is None else lambda1_mask
+    Theta_0 = Omega_0.copy() if Theta_0 is None else Theta_0
+    X_0 = np.zeros((p, p)) if X_0 is None else X_0
+    numC, allC = get_connected_components(S, lambda1 * mask)
+    owner = assign_blocks([len(C) for C in allC], world)
+    mine = [ci for ci in range(numC) if owner[ci] == rank]
+    kw = dict(tol=tol, rtol=rtol, stopping_criterion=stopping_criterion, update_rho=update_rho, rho=rho,
+              max_iter=max_iter, verbose=False, measure=False)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol = _solve_components(S, lambda1, mask, Omega_0, Theta_0, X_0, allC, mine, kw, solver=solver)
+    if world > 1:
+        use_cuda = dist.get_backend(group) == "nccl"
+        for k in ("Omega", "Theta", "X"):
+            t = torch.from_numpy(sol[k])
+            if use_cuda:
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            sol[k] = t.cpu().numpy()
+    return sol
+
+
 def assign_blocks(sizes, world):
     """longest-processing-time assignment of connected components (cost ~ size^3) to ranks."""
     order = np.argsort(-np.asarray(sizes, dtype=float) ** 3, kind="stable")

@@ -144,13 +144,23 @@ def block_SGL(S: np.ndarray,
         X_0 = np.zeros((p, p))
 
     numC, allC = get_connected_components(S, lambda1 * lambda1_mask)
-
-    sol = {'Omega': np.zeros((p, p)), 'Theta': np.zeros((p, p)), 'X': np.zeros((p, p))}
     kw = dict(tol=tol, rtol=rtol, stopping_criterion=stopping_criterion, update_rho=update_rho, rho=rho,
               max_iter=max_iter, verbose=verbose, measure=measure)
+    return _solve_components(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, allC, range(numC), kw)
+
+
+def _solve_components(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, allC, mine, kw, solver=None):
+    """solve the components with indices ``mine`` (all of them for block_SGL, this rank's share for
+    parallel.block_SGL_dist) and scatter them into (p,p) arrays that are zero elsewhere."""
+    p = S.shape[0]
+    mine = set(mine)
+    stopping_criterion, verbose, measure = kw["stopping_criterion"], kw["verbose"], kw["measure"]
+    sol = {'Omega': np.zeros((p, p)), 'Theta': np.zeros((p, p)), 'X': np.zeros((p, p))}
     lines = {}
-    multi = [ci for ci, C in enumerate(allC) if len(C) > 1]
+    multi = [ci for ci, C in enumerate(allC) if len(C) > 1 and ci in mine]
     for ci, C in enumerate(allC):
+        if ci not in mine:
+            continue
         if len(C) == 1:
             # single node components have a closed form solution (off-diagonal penalty only)
             closed_sol = 1 / S[C, C]
@@ -159,7 +169,7 @@ def block_SGL(S: np.ndarray,
 
     # Components that fit the shared-memory eigensolver are solved as ragged batches (one CTA per block and
     # kernel, per-block rho / stopping test on the device); larger ones one by one on the large-p path.
-    batchable = stopping_criterion == "boyd" and not verbose and not measure
+    batchable = stopping_criterion == "boyd" and not verbose and not measure and solver is None
     small = [ci for ci in multi if len(allC[ci]) <= _BATCH_MAX] if batchable else []
     large = [ci for ci in multi if ci not in set(small)]
     for bucket in _size_buckets([len(allC[ci]) for ci in small]):
@@ -170,7 +180,7 @@ def block_SGL(S: np.ndarray,
         ix = np.ix_(C, C)
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
-            block_sol, _ = ADMM_SGL(S=np.ascontiguousarray(S[ix]),
+            block_sol, _ = (solver or ADMM_SGL)(S=np.ascontiguousarray(S[ix]),
                                     lambda1=lambda1,
                                     Omega_0=np.ascontiguousarray(Omega_0[ix]),
                                     Theta_0=np.ascontiguousarray(Theta_0[ix]),

@@ -79,6 +79,13 @@ int gg_prox_sgl(const double* Omega, const double* Omega_prev, const double* L, 
                 double* C, const double* ctrl, double lam, const double* lam_mat, int M, int p,
                 double* partials, const int* pvec, void* stream);
 
+/* Functional SGL: Theta = prox_sum_Frob(Omega + L + X, Mblk, lam/rho)   src/gglasso/solver/ggl_helper.py:45-66,
+ * src/gglasso/solver/functional_sgl_admm.py:148.  Off-diagonal Mblk x Mblk blocks are shrunk in Frobenius norm.
+ * blk_nrm: scratch, M * (p/Mblk)^2 doubles.  Same fusion / latent convention as gg_prox_sgl. */
+int gg_prox_fsgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
+                 double* C, const double* ctrl, double lam, int Mblk, int M, int p, double* partials,
+                 double* blk_nrm, void* stream);
+
 /* Theta = prox_p(Omega + L + X, lambda1/rho, lambda2/rho, reg)   src/gglasso/solver/ggl_helper.py:190-207
  * reg 0 = GGL (ggl_helper.py:68-71,38-43), 1 = FGL (ggl_helper.py:131-134, fgl_helper.py:11-68).
  * Same fusion/latent convention as gg_prox_sgl; partials: gg_mgl_ntile(p)^2 * GG_NPART doubles,

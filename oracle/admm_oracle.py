@@ -23,6 +23,8 @@ Every function cites the reference lines it follows (paths relative to /root/ref
   admm_mgl              src/gglasso/solver/admm_solver.py:13-313
   admm_sgl              src/gglasso/solver/single_admm_solver.py:15-275
   block_sgl             src/gglasso/solver/single_admm_solver.py:326-475 (+ get_connected_components :478-490)
+  prox_sum_frob         src/gglasso/solver/ggl_helper.py:45-66
+  admm_fsgl             src/gglasso/solver/functional_sgl_admm.py:12-239
 
 Third-party arithmetic the reference delegates to (not under /root/reference): numpy.linalg.eigh
 (LAPACK dsyevd), numpy matmul (dgemm), scipy.sparse.csgraph.connected_components.  The oracle
@@ -461,3 +463,66 @@ def block_sgl(S, lambda1, Omega_0, Theta_0=None, X_0=None, rho=1.0, max_iter=100
             for k in out:
                 out[k][ix] = bs[k]
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# functional SGL
+# ----------------------------------------------------------------------------------------
+def prox_sum_frob(X, M, l):
+    """off-diagonal MxM blocks shrunk in Frobenius norm (from the upper block, mirrored); diagonal blocks kept."""
+    pM = X.shape[0]
+    assert pM % M == 0
+    p = pM // M
+    Y = np.zeros((pM, pM))
+    for i in range(p):
+        for j in range(i, p):
+            blk = X[i * M:(i + 1) * M, j * M:(j + 1) * M]
+            if i == j:
+                Y[i * M:(i + 1) * M, j * M:(j + 1) * M] = blk
+            else:
+                a = max(np.linalg.norm(blk), l)
+                B = blk * (a - l) / a
+                Y[i * M:(i + 1) * M, j * M:(j + 1) * M] = B
+                Y[j * M:(j + 1) * M, i * M:(i + 1) * M] = B.T
+    return Y
+
+
+def admm_fsgl(S, lambda1, M, Omega_0, Theta_0=None, X_0=None, rho=1.0, max_iter=1000, tol=1e-7, rtol=1e-4,
+              update_rho=True, measure=False, latent=False, mu1=None, trace=None):
+    """ADMM for the functional single graphical lasso; returns (sol, info)."""
+    assert Omega_0.shape == S.shape and S.shape[0] == S.shape[1] and lambda1 > 0 and rho > 0
+    pM = S.shape[0]
+    assert pM % M == 0
+    Omega = Omega_0.copy()
+    Theta = Omega_0.copy() if Theta_0 is None or len(Theta_0) == 0 else Theta_0.copy()
+    X = np.zeros((pM, pM)) if X_0 is None or len(X_0) == 0 else X_0.copy()
+    L = np.zeros((pM, pM))
+    residual = np.zeros(max_iter)
+    status = ""
+    for it in range(max_iter):
+        W = Theta - L - X - (1 / rho) * S
+        D, Q = np.linalg.eigh(W)
+        Omega_prev = Omega.copy()
+        Omega = phiplus(1 / rho, D, Q)
+        Theta = prox_sum_frob(Omega + L + X, M, (1 / rho) * lambda1)
+        if latent:
+            C = Theta - X - Omega
+            D1, Q1 = np.linalg.eigh(C)
+            L = prox_rank_norm(D1, Q1, mu1 / rho)
+        X = X + Omega - Theta + L
+        r, s, e_pri, e_dual = boyd_residuals(Omega, Omega_prev, Theta, L, X, rho, tol, rtol)
+        if trace is not None:
+            trace.append(dict(rho=rho, r=r, s=s, e_pri=e_pri, e_dual=e_dual))
+        if update_rho:
+            rho_new = _rho_update(r, s, rho)
+            X = (rho / rho_new) * X
+            rho = rho_new
+        residual[it] = max(r, s)
+        if r <= e_pri and s <= e_dual:
+            status = "optimal"
+            break
+    status = _final_status(status, "boyd", r, s, e_pri, e_dual)
+    sol = {"Omega": Omega, "Theta": Theta, "X": X}
+    if latent:
+        sol["L"] = L
+    return sol, {"status": status, "iterations": it + 1, "residual": residual[:it + 1], "rho": rho}

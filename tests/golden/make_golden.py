@@ -163,5 +163,35 @@ def main():
          Theta_full=full["Theta"])
 
 
+def fsgl_fixtures():
+    """functional SGL (src/gglasso/solver/functional_sgl_admm.py): M=3 blocks, with and without latent, + prox."""
+    import gglasso.solver.functional_sgl_admm as ref_f
+    rng = np.random.default_rng(77)
+    p, M, N = 12, 3, 400
+    pM = p * M
+    A = rng.standard_normal((pM, pM)) * (rng.random((pM, pM)) < 0.08)
+    Prec = A @ A.T * 0.3 + np.eye(pM)
+    Sigma = np.linalg.inv(Prec)
+    X = rng.multivariate_normal(np.zeros(pM), Sigma, N).T
+    S = np.cov(X, bias=True)
+    Y = rng.standard_normal((pM, pM))
+    Y = Y + Y.T
+    out = dict(S=S, M=M, lambda1=0.05, prox_in=Y, prox_out=gh.prox_sum_Frob(Y, M, 0.7))
+    for lat in (False, True):
+        with Capture(ref_f) as cap:
+            sol, info = quiet(ref_f.ADMM_FSGL, S, 0.05, M, np.eye(pM), tol=1e-7, rtol=1e-7, measure=True,
+                              latent=lat, mu1=0.2 if lat else None)
+        tag = "lat" if lat else "nolat"
+        out.update({f"Theta_{tag}": sol["Theta"], f"Omega_{tag}": sol["Omega"], f"X_{tag}": sol["X"],
+                    f"traj_{tag}": cap.table(), f"status_{tag}": info["status"], f"residual_{tag}": info["residual"]})
+        if lat:
+            out["L_lat"] = sol["L"]
+    save("fsgl_p12_M3", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fsgl":
+        fsgl_fixtures()
+    else:
+        main()
+        fsgl_fixtures()

@@ -503,3 +503,39 @@ def test_grid_search_device_resident_matches_host_driver():
         assert _rel(best_d[k], best_h[k]) < PER_ITER_TOL, k
     sc_a, _, _, _ = grid_search_device(S, np.full(K, N), "FGL", l1[:1], l2[:1], method="AIC")
     assert np.isfinite(sc_a).all()
+
+
+def test_admm_fsgl_vs_reference_golden(golden):
+    """functional SGL (block-Frobenius prox) vs the real reference's output, with and without latent variables."""
+    from gglasso_b200 import ADMM_FSGL
+    g = golden("fsgl_p12_M3")
+    S, M, lam = g["S"], int(g["M"]), float(g["lambda1"])
+    pM = S.shape[0]
+    for tag, lat in (("nolat", False), ("lat", True)):
+        (sol, info), out = _quiet(ADMM_FSGL, S, lam, M, np.eye(pM), tol=1e-7, rtol=1e-7, measure=True, latent=lat,
+                                  mu1=0.2 if lat else None)
+        n = g[f"traj_{tag}"].shape[0]
+        assert info["status"] == str(g[f"status_{tag}"]) and len(info["residual"]) == n
+        assert f"ADMM terminated after {n} iterations" in out
+        np.testing.assert_allclose(info["residual"], g[f"residual_{tag}"], rtol=1e-7, atol=1e-12)
+        for k in ("Theta", "Omega", "X"):
+            ref = g[f"{k}_{tag}"]
+            assert np.linalg.norm(sol[k] - ref) <= PER_ITER_TOL * max(1.0, np.linalg.norm(ref)), (tag, k)
+        assert np.array_equal(sol["Theta"] != 0, g[f"Theta_{tag}"] != 0)
+        assert ("L" in sol) == lat
+    assert np.linalg.norm(sol["L"] - g["L_lat"]) <= PER_ITER_TOL * max(1.0, np.linalg.norm(g["L_lat"]))
+
+
+def test_admm_fsgl_M1_equals_sgl_and_verbose_format():
+    """reference tests/test_func_gl.py: for M=1 the functional solver is the single graphical lasso."""
+    from gglasso_b200 import ADMM_FSGL, ADMM_SGL
+    rng = np.random.default_rng(123)
+    p = 20
+    S = np.cov(rng.standard_normal((p, 100)), bias=True)
+    (s1, _), _ = _quiet(ADMM_SGL, S, 0.01, np.eye(p), tol=1e-10, rtol=1e-10)
+    (s2, _), out = _quiet(ADMM_FSGL, S, 0.01, 1, np.eye(p), tol=1e-10, rtol=1e-10, verbose=True)
+    assert np.abs(s1["Theta"] - s2["Theta"]).max() < 1e-9
+    lines = out.splitlines()
+    assert lines[0] == f"Derived a Functional SGL problem of dimensionality p={p}."
+    assert lines[2] == "%4s\t%10s\t%10s\t%10s\t%10s\t%10s" % ("iter", "r_t", "s_t", "eps_pri", "eps_dual", "rho")
+    assert len(lines[3].split("\t")) == 6

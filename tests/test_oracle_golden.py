@@ -134,3 +134,21 @@ def test_mask_of_zeros_gives_inverse():
     S = A.T @ A / (4 * p)
     sol, info = orc.admm_sgl(S, 0.1, np.eye(p), tol=1e-10, rtol=1e-10, lambda1_mask=np.zeros((p, p)))
     np.testing.assert_allclose(sol["Theta"], np.linalg.inv(S), atol=1e-4)
+
+
+def test_fsgl_matches_reference(golden):
+    g = golden("fsgl_p12_M3")
+    S, M, lam = g["S"], int(g["M"]), float(g["lambda1"])
+    assert _rel(orc.prox_sum_frob(g["prox_in"], M, 0.7), g["prox_out"]) < 1e-15
+    for tag, lat in (("nolat", False), ("lat", True)):
+        trace = []
+        sol, info = orc.admm_fsgl(S, lam, M, np.eye(S.shape[0]), tol=1e-7, rtol=1e-7, latent=lat,
+                                  mu1=0.2 if lat else None, trace=trace)
+        traj = g[f"traj_{tag}"]
+        assert info["status"] == str(g[f"status_{tag}"]) and len(trace) == traj.shape[0]
+        assert np.array_equal(np.array([t["rho"] for t in trace]), traj[:, 0])
+        np.testing.assert_allclose(info["residual"], g[f"residual_{tag}"], rtol=1e-7, atol=1e-13)
+        for k in ("Theta", "Omega", "X"):
+            assert np.linalg.norm(sol[k] - g[f"{k}_{tag}"]) <= RTOL * max(1.0, np.linalg.norm(g[f"{k}_{tag}"])), k
+        assert np.array_equal(sol["Theta"] != 0, g[f"Theta_{tag}"] != 0)
+    assert np.linalg.norm(sol["L"] - g["L_lat"]) <= RTOL * max(1.0, np.linalg.norm(g["L_lat"]))

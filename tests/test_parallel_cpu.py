@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gglasso_b200.parallel import KShard, assign_blocks, ebic_mgl, grid_search_dist, partition
+from gglasso_b200.parallel import KShard, assign_blocks, block_SGL_dist, ebic_mgl, grid_search_dist, partition
 
 
 def _free_port():
@@ -134,3 +134,52 @@ def test_assign_blocks_lpt():
         load[o] += s ** 3
     assert load.max() == 1289 ** 3                    # nothing else lands on the big block's rank
     assert set(assign_blocks([5, 5, 5, 5], 2)) == {0, 1}
+
+
+def _oracle_sgl(S, lambda1, Omega_0, Theta_0=None, X_0=None, **kw):
+    from oracle import admm_oracle as orc
+    kw.pop("verbose", None)
+    return orc.admm_sgl(S, lambda1, Omega_0, Theta_0, X_0, **kw)
+
+
+def _block_inputs():
+    rng = np.random.default_rng(4)
+    sizes = [1, 2, 3, 6, 9, 1, 4]
+    p = sum(sizes)
+    S = np.zeros((p, p))
+    o = 0
+    for s in sizes:
+        Z = rng.standard_normal((s, 3 * s + 4))
+        B = Z @ Z.T / (3 * s + 4)
+        S[o:o + s, o:o + s] = 0.5 * B / np.sqrt(np.outer(np.diag(B), np.diag(B))) + 0.5 * np.eye(s)
+        o += s
+    perm = rng.permutation(p)
+    return S[np.ix_(perm, perm)], 0.02
+
+
+def _block_worker(rank, world, port, q):
+    _init(rank, world, port)
+    try:
+        S, lam = _block_inputs()
+        sol = block_SGL_dist(S, lam, np.eye(S.shape[0]), tol=1e-8, rtol=1e-8, solver=_oracle_sgl)
+        q.put((rank, sol["Theta"], sol["Omega"], sol["X"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_block_sgl_distributed_gloo_ws2_matches_oracle():
+    from oracle import admm_oracle as orc
+    S, lam = _block_inputs()
+    ref = orc.block_sgl(S, lam, np.eye(S.shape[0]), tol=1e-8, rtol=1e-8)
+    one = block_SGL_dist(S, lam, np.eye(S.shape[0]), tol=1e-8, rtol=1e-8, solver=_oracle_sgl)   # world = 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_block_worker, args=(r, 2, port, q)) for r in range(2)]
+    [pr.start() for pr in procs]
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    [pr.join(timeout=60) for pr in procs]
+    for got in [(0, one["Theta"], one["Omega"], one["X"])] + res:
+        np.testing.assert_allclose(got[1], ref["Theta"], atol=1e-12)
+        np.testing.assert_allclose(got[2], ref["Omega"], atol=1e-12)
+        np.testing.assert_allclose(got[3], ref["X"], atol=1e-12)
