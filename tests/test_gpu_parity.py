@@ -539,3 +539,39 @@ def test_admm_fsgl_M1_equals_sgl_and_verbose_format():
     assert lines[0] == f"Derived a Functional SGL problem of dimensionality p={p}."
     assert lines[2] == "%4s\t%10s\t%10s\t%10s\t%10s\t%10s" % ("iter", "r_t", "s_t", "eps_pri", "eps_dual", "rho")
     assert len(lines[3].split("\t")) == 6
+
+
+def test_cfg3_full_size_first_iterations_vs_oracle():
+    """BASELINE cfg3 at full size (FGL, K=20, p=1000): the first two ADMM iterations against the CPU oracle
+    (per-iteration bar: 1e-8 relative Frobenius, identical sparsity pattern), plus size-independent properties."""
+    from gglasso_b200 import ADMM_MGL
+    from gglasso_b200.datagen import synthetic_mgl
+    from oracle import admm_oracle as orc
+    K, p = 20, 1000
+    S = synthetic_mgl(K, p, N=2000, seed=1234, kind="fused")
+    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    kw = dict(tol=1e-7, rtol=1e-7, max_iter=2)
+    (sol, info), _ = _quiet(ADMM_MGL, S, 0.05, 0.01, "FGL", Om0, **kw)
+    ref, rinfo = orc.admm_mgl(S, 0.05, 0.01, "FGL", Om0, **kw)
+    assert info["status"] == rinfo["status"] == "max iterations reached"
+    for k in ("Omega", "Theta", "X"):
+        assert _rel(sol[k], ref[k]) < PER_ITER_TOL, k
+    assert np.array_equal(sol["Theta"] != 0, ref["Theta"] != 0)
+    # properties: Theta exactly symmetric with untouched diagonal structure, Omega symmetric positive definite
+    assert np.array_equal(sol["Theta"], sol["Theta"].transpose(0, 2, 1))
+    assert np.array_equal(sol["Omega"], sol["Omega"].transpose(0, 2, 1))
+    assert np.linalg.eigvalsh(sol["Omega"][::7]).min() > 0
+
+
+@pytest.mark.parametrize("M,p", [(1, 1289), (2, 2047)])
+def test_eigh_large_odd_sizes(M, p):
+    """sizes that are neither multiples of the tile sizes nor powers of two (multi-level D&C, ragged tiles)."""
+    from gglasso_b200._engine import eigh
+    from gglasso_b200.datagen import synthetic_mgl
+    A = np.eye(p)[None] - synthetic_mgl(M, p, N=2 * p, seed=4)
+    D, Q = eigh(A)
+    Dref = np.linalg.eigvalsh(A)
+    assert np.abs(D - Dref).max() < 1e-11 * p ** 0.5
+    for m in range(M):
+        assert np.abs(Q[m].T @ Q[m] - np.eye(p)).max() < 1e-12
+        assert np.abs(A[m] @ Q[m] - Q[m] * D[m]).max() < 1e-11
