@@ -9,6 +9,7 @@ dicts), backed by hand-written CUDA kernels behind a C ABI (include/gglasso_b200
 from .solver.admm_solver import ADMM_MGL  # noqa: F401
 from .solver.single_admm_solver import ADMM_SGL, block_SGL, get_connected_components  # noqa: F401
 from .solver.functional_sgl_admm import ADMM_FSGL  # noqa: F401
+from .solver.ext_admm_solver import ext_ADMM_MGL  # noqa: F401
 from ._lib import GGLassoB200Error, LIB_PATH  # noqa: F401
 
 __version__ = "0.1.0"
@@ -25,10 +26,12 @@ def install():
     targets = {
         "gglasso.solver.admm_solver": {"ADMM_MGL": ADMM_MGL},
         "gglasso.solver.single_admm_solver": {"ADMM_SGL": ADMM_SGL, "block_SGL": block_SGL},
-        "gglasso.problem": {"ADMM_MGL": ADMM_MGL, "ADMM_SGL": ADMM_SGL, "block_SGL": block_SGL},
+        "gglasso.problem": {"ADMM_MGL": ADMM_MGL, "ADMM_SGL": ADMM_SGL, "block_SGL": block_SGL,
+                            "ext_ADMM_MGL": ext_ADMM_MGL},
         "gglasso.helper.model_selection": {"ADMM_SGL": ADMM_SGL, "block_SGL": block_SGL},
         "gglasso.solver.ppdna_solver": {"ADMM_MGL": ADMM_MGL},
         "gglasso.solver.functional_sgl_admm": {"ADMM_FSGL": ADMM_FSGL},
+        "gglasso.solver.ext_admm_solver": {"ext_ADMM_MGL": ext_ADMM_MGL},
     }
     for modname, names in targets.items():
         try:

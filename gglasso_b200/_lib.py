@@ -32,6 +32,9 @@ SIGNATURES = {
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "gg_prox_band": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, _i, _i, _i, _vp]),
+    "gg_ext_theta": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "gg_ext_lambda": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
+    "gg_ext_dual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "gg_dual_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gg_stop_update": (_i, [_vp, _i, _vp, _vp, _i, _vp, _d, _d, _i, _i, _vp]),
     "gg_scale_pending": (_i, [_vp, _vp, _i, _i, _i, _vp]),

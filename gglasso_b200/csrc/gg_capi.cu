@@ -25,6 +25,12 @@ int gg_eigh_impl(double*, double*, int, int, const double*, int, void*, size_t, 
 
 int gg_eigh_tridiag_impl(double*, double*, int, int, const double*, int, void*, size_t, cudaStream_t, int);
 int gg_launch_add3(const double*, const double*, const double*, double*, size_t, cudaStream_t);
+int gg_launch_ext_theta(const double*, const double*, const double*, const double*, const double*, const double*,
+                        const double*, int, int, double*, double*, cudaStream_t);
+int gg_launch_ext_lambda(const double*, const double*, const int*, int, int, int, double, const double*, double*,
+                         cudaStream_t);
+int gg_launch_ext_dual(double*, double*, const double*, const double*, const double*, const double*, const double*,
+                       const double*, const double*, const int*, int, int, double*, cudaStream_t);
 int gg_launch_prox_band(const double*, double*, const double*, double, double, int, int, int, int, int, cudaStream_t);
 size_t gg_tridiag_ws_bytes(int, int);
 
@@ -137,6 +143,29 @@ int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lamb
 {
     if (K <= 0 || nb < 0 || p <= 0 || reg < 0 || reg > 1) return -1;
     return gg_launch_prox_band(V, Theta, ctrl, lambda1, lambda2, reg, K, nb, p, row0, (cudaStream_t)stream);
+}
+
+int gg_ext_theta(const double* Omega, const double* L, const double* X0, const double* Lam, const double* X1,
+                 const double* lam1, const double* ctrl, int K, int p, double* Theta, double* C, void* stream)
+{
+    if (K <= 0 || p <= 0) return -1;
+    return gg_launch_ext_theta(Omega, L, X0, Lam, X1, lam1, ctrl, K, p, Theta, C, (cudaStream_t)stream);
+}
+
+int gg_ext_lambda(const double* Theta, const double* X1, const int* G, int Lg, int K, int p, double lambda2,
+                  const double* ctrl, double* Lam, void* stream)
+{
+    if (K <= 0 || p <= 0 || Lg < 0) return -1;
+    return gg_launch_ext_lambda(Theta, X1, G, Lg, K, p, lambda2, ctrl, Lam, (cudaStream_t)stream);
+}
+
+int gg_ext_dual(double* X0, double* X1, const double* Omega, const double* Omega_prev, const double* Theta,
+                const double* L, const double* Lam, const double* Lam_prev, const double* ctrl, const int* pvec,
+                int K, int p, double* partials, void* stream)
+{
+    if (K <= 0 || p <= 0) return -1;
+    return gg_launch_ext_dual(X0, X1, Omega, Omega_prev, Theta, L, Lam, Lam_prev, ctrl, pvec, K, p, partials,
+                              (cudaStream_t)stream);
 }
 
 void gg_host_tv1d(double* v, int n, int stride, double lam) { gg_tv1d_inplace(v, n, stride, lam); }

@@ -502,6 +502,124 @@ prox_band_kernel(const double* __restrict__ V, double* __restrict__ Theta, const
     for (int k = 0; k < K; ++k) Theta[k * slab + e] = y[k * T];
 }
 
+// ------------------------------------------------------------------------------------------
+// ext_ADMM_MGL (non-conforming group graphical lasso, src/gglasso/solver/ext_admm_solver.py:191-273).
+// The K matrices of different size p_k are padded to a common p (decoupled unit diagonal, see block_SGL);
+// pvec[k] = p_k masks the padding out of the norms.  One ADMM problem, rho fixed.
+//
+// Theta update: V = (Omega + L + X0 + Lambda - X1)/2, Theta = prox_od_1norm(V, lambda1_k/(2 rho))   (:206-208)
+// latent: C = Theta - X0 - Omega                                                                   (:212-216)
+__global__ void __launch_bounds__(EW_THREADS)
+ext_theta_kernel(const double* __restrict__ Omega, const double* __restrict__ L, const double* __restrict__ X0,
+                 const double* __restrict__ Lam, const double* __restrict__ X1, const double* __restrict__ lam1,
+                 const double* __restrict__ ctrl, int p, double* __restrict__ Theta, double* __restrict__ C)
+{
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const int m = blockIdx.y;
+    const double thr = lam1[m] / (2.0 * ctrl[GG_C_RHO]);
+    const size_t pp = (size_t)p * p, base = (size_t)m * pp;
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
+        const double om = Omega[base + e], x0 = X0[base + e];
+        double v = om;
+        if (L) v = v + L[base + e];
+        v = v + x0;
+        v = v + Lam[base + e];
+        v = (v - X1[base + e]) * 0.5;
+        const double th = (i == j) ? v : gg_soft(v, thr);
+        Theta[base + e] = th;
+        if (C) C[base + e] = (th - x0) - om;
+    }
+}
+
+// Lambda = prox_2norm_G(Theta + X1, G, lambda2/rho)   (:219-223, :394-453).  Step 1 copies Z = Theta + X1;
+// step 2: one thread per group l gathers the member entries (G[0,l,k], G[1,l,k]) != -1 over k, shrinks the
+// vector in Euclidean norm with threshold (lambda2/rho) sqrt(group size) and scatters it to (i,j) and (j,i).
+__global__ void __launch_bounds__(EW_THREADS)
+ext_z_kernel(const double* __restrict__ Theta, const double* __restrict__ X1, const double* __restrict__ ctrl,
+             size_t total, double* __restrict__ Z)
+{
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * EW_THREADS)
+        Z[e] = Theta[e] + X1[e];
+}
+
+__global__ void __launch_bounds__(128)
+ext_group_prox_kernel(const double* __restrict__ Theta, const double* __restrict__ X1, const int* __restrict__ G,
+                      int Lg, int K, int p, double lambda2, const double* __restrict__ ctrl, double* __restrict__ Lam)
+{
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= Lg) return;
+    const size_t pp = (size_t)p * p;
+    const int* Gi = G + (size_t)l * K;                 // G[0,l,:]
+    const int* Gj = G + (size_t)Lg * K + (size_t)l * K;  // G[1,l,:]
+    double ss = 0.0;
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) {
+        const int i = Gi[k];
+        if (i < 0) continue;
+        const size_t e = (size_t)k * pp + (size_t)i * p + Gj[k];
+        const double v = Theta[e] + X1[e];
+        ss += v * v;
+        ++cnt;
+    }
+    const double lam = (lambda2 / ctrl[GG_C_RHO]) * sqrt((double)cnt);
+    const double nrm = sqrt(ss);
+    const double a = nrm > lam ? nrm : lam;
+    for (int k = 0; k < K; ++k) {
+        const int i = Gi[k];
+        if (i < 0) continue;
+        const int j = Gj[k];
+        const size_t e = (size_t)k * pp + (size_t)i * p + j;
+        const double v = Theta[e] + X1[e];
+        const double z = (v * (a - lam)) / a;
+        Lam[e] = z;
+        Lam[(size_t)k * pp + (size_t)j * p + i] = z;
+    }
+}
+
+// X0 += Omega - Theta + L ; X1 += Theta - Lambda ; residual partial sums of the ext criterion (:330-347):
+//   [0] |Omega|^2+|Lambda|^2  [1] |Theta-L|^2+|Theta|^2  [2] |X0|^2+|X1|^2
+//   [3] |Omega-Theta+L|^2+|Lambda-Theta|^2  [4] |Omega-Omega_prev|^2+|Lambda-Lambda_prev|^2
+__global__ void __launch_bounds__(EW_THREADS)
+ext_dual_kernel(double* __restrict__ X0, double* __restrict__ X1, const double* __restrict__ Omega,
+                const double* __restrict__ Omega_prev, const double* __restrict__ Theta, const double* __restrict__ L,
+                const double* __restrict__ Lam, const double* __restrict__ Lam_prev, const double* __restrict__ ctrl,
+                const int* __restrict__ pvec, int p, double* __restrict__ partials)
+{
+    __shared__ double scratch[GG_NPART * 32];
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const int m = blockIdx.y;
+    const int pb = pvec ? pvec[m] : p;
+    const size_t pp = (size_t)p * p, base = (size_t)m * pp;
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int i = (int)(e / p), j = (int)(e - (size_t)i * p);
+        const double om = Omega[base + e], th = Theta[base + e], la = Lam[base + e];
+        const double l = L ? L[base + e] : 0.0;
+        const double r0 = L ? ((om - th) + l) : (om - th);
+        const double r1 = th - la;
+        const double x0 = X0[base + e] + r0, x1 = X1[base + e] + r1;
+        X0[base + e] = x0;
+        X1[base + e] = x1;
+        if (i < pb && j < pb) {
+            const double tl = th - l, d0 = om - Omega_prev[base + e], d1 = la - Lam_prev[base + e];
+            acc[0] += om * om + la * la;
+            acc[1] += tl * tl + th * th;
+            acc[2] += x0 * x0 + x1 * x1;
+            acc[3] += r0 * r0 + r1 * r1;
+            acc[4] += d0 * d0 + d1 * d1;
+        }
+    }
+    gg_block_sum<GG_NPART>(acc, scratch);
+    if (threadIdx.x == 0) {
+        double* out = partials + ((size_t)m * gridDim.x + blockIdx.x) * GG_NPART;
+#pragma unroll
+        for (int q = 0; q < GG_NPART; ++q) out[q] = acc[q];
+    }
+}
+
 // ==========================================================================================
 // host launchers (C++ linkage; the extern "C" ABI lives in gg_capi.cu)
 // ==========================================================================================
@@ -655,6 +773,41 @@ int gg_launch_prox_band(const double* V, double* Theta, const double* ctrl, doub
         if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         prox_band_kernel<1><<<grid, T, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
     }
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_ext_theta(const double* Omega, const double* L, const double* X0, const double* Lam, const double* X1,
+                        const double* lam1, const double* ctrl, int K, int p, double* Theta, double* C, cudaStream_t st)
+{
+    dim3 grid(gg_sgl_nparts(p, K), K);
+    ext_theta_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, L, X0, Lam, X1, lam1, ctrl, p, Theta, C);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_ext_lambda(const double* Theta, const double* X1, const int* G, int Lg, int K, int p, double lambda2,
+                         const double* ctrl, double* Lam, cudaStream_t st)
+{
+    const size_t total = (size_t)K * p * p;
+    size_t blocks = (total + EW_THREADS - 1) / EW_THREADS;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ext_z_kernel<<<(unsigned)blocks, EW_THREADS, 0, st>>>(Theta, X1, ctrl, total, Lam);
+    GG_CHECK_LAUNCH();
+    if (Lg > 0) {
+        ext_group_prox_kernel<<<(Lg + 127) / 128, 128, 0, st>>>(Theta, X1, G, Lg, K, p, lambda2, ctrl, Lam);
+        GG_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int gg_launch_ext_dual(double* X0, double* X1, const double* Omega, const double* Omega_prev, const double* Theta,
+                       const double* L, const double* Lam, const double* Lam_prev, const double* ctrl,
+                       const int* pvec, int K, int p, double* partials, cudaStream_t st)
+{
+    dim3 grid(gg_sgl_nparts(p, K), K);
+    ext_dual_kernel<<<grid, EW_THREADS, 0, st>>>(X0, X1, Omega, Omega_prev, Theta, L, Lam, Lam_prev, ctrl, pvec, p,
+                                                 partials);
     GG_CHECK_LAUNCH();
     return 0;
 }

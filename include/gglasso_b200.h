@@ -102,6 +102,20 @@ int gg_add3(const double* Omega, const double* L, const double* X, double* V, si
 int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lambda1, double lambda2, int reg,
                  int K, int nb, int p, int row0, void* stream);
 
+/* ext_ADMM_MGL, non-conforming group graphical lasso (src/gglasso/solver/ext_admm_solver.py:191-273, :330-347,
+ * :394-453).  The K matrices of size p_k are padded to (K,p,p); pvec[k] = p_k; one problem (ctrl block 0), rho fixed.
+ *  gg_ext_theta : Theta = prox_od_1norm((Omega+L+X0+Lambda-X1)/2, lam1[k]/(2 rho)); C = Theta-X0-Omega if C != NULL
+ *  gg_ext_lambda: Lambda = prox_2norm_G(Theta + X1, G, lambda2/rho); G is the reference's (2,Lg,K) int array
+ *  gg_ext_dual  : X0 += Omega-Theta+L, X1 += Theta-Lambda, partial sums laid out for gg_stop_update (nparts =
+ *                 K * gg_sgl_nparts(p,K)) */
+int gg_ext_theta(const double* Omega, const double* L, const double* X0, const double* Lam, const double* X1,
+                 const double* lam1, const double* ctrl, int K, int p, double* Theta, double* C, void* stream);
+int gg_ext_lambda(const double* Theta, const double* X1, const int* G, int Lg, int K, int p, double lambda2,
+                  const double* ctrl, double* Lam, void* stream);
+int gg_ext_dual(double* X0, double* X1, const double* Omega, const double* Omega_prev, const double* Theta,
+                const double* L, const double* Lam, const double* Lam_prev, const double* ctrl, const int* pvec,
+                int K, int p, double* partials, void* stream);
+
 /* X += Omega - Theta + L and partial sums (latent variants; L may be NULL for the K-sharded non-latent loop)   admm_solver.py:208, single_admm_solver.py:177.
  * sgl_order selects the association order of the reference's SGL expression. */
 int gg_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta,

@@ -25,6 +25,8 @@ Every function cites the reference lines it follows (paths relative to /root/ref
   block_sgl             src/gglasso/solver/single_admm_solver.py:326-475 (+ get_connected_components :478-490)
   prox_sum_frob         src/gglasso/solver/ggl_helper.py:45-66
   admm_fsgl             src/gglasso/solver/functional_sgl_admm.py:12-239
+  prox_2norm_G          src/gglasso/solver/ext_admm_solver.py:394-453
+  ext_admm_mgl          src/gglasso/solver/ext_admm_solver.py:18-392
 
 Third-party arithmetic the reference delegates to (not under /root/reference): numpy.linalg.eigh
 (LAPACK dsyevd), numpy matmul (dgemm), scipy.sparse.csgraph.connected_components.  The oracle
@@ -526,3 +528,105 @@ def admm_fsgl(S, lambda1, M, Omega_0, Theta_0=None, X_0=None, rho=1.0, max_iter=
     if latent:
         sol["L"] = L
     return sol, {"status": status, "iterations": it + 1, "residual": residual[:it + 1], "rho": rho}
+
+
+# ----------------------------------------------------------------------------------------
+# non-conforming group graphical lasso (ext_ADMM_MGL)
+# ----------------------------------------------------------------------------------------
+def prox_2norm_G(X, G, l2):
+    """group prox through the bookkeeping array G (2,L,K): per group l the member entries X[k][G0,G1] (G != -1)
+    are shrunk in Euclidean norm with threshold l2*sqrt(group size) and written back symmetrically."""
+    K = len(X)
+    out = [X[k].copy() for k in range(K)]
+    for l in range(G.shape[1]):
+        ks = [k for k in range(K) if G[0, l, k] != -1]
+        v = np.array([out[k][G[0, l, k], G[1, l, k]] for k in ks])
+        lam = l2 * np.sqrt(len(ks))
+        a = max(np.sqrt((v ** 2).sum()), lam)
+        z = v * (a - lam) / a
+        for k, zk in zip(ks, z):
+            out[k][G[0, l, k], G[1, l, k]] = zk
+            out[k][G[1, l, k], G[0, l, k]] = zk
+    return dict(enumerate(out))
+
+
+def ext_admm_mgl(S, lambda1, lambda2, Omega_0, G, X0=None, X1=None, tol=1e-5, rtol=1e-4, stopping_criterion="boyd",
+                 rho=1.0, max_iter=1000, latent=False, mu1=None):
+    """ADMM for the group graphical lasso with non-conforming dimensions (dicts keyed 0..K-1)."""
+    K = len(S)
+    p = np.array([S[k].shape[0] for k in range(K)])
+    lam1 = lambda1 * np.ones(K) if np.isscalar(lambda1) else np.asarray(lambda1, dtype=float)
+    if latent:
+        mu = mu1 * np.ones(K) if np.isscalar(mu1) else np.asarray(mu1, dtype=float)
+    Omega = {k: Omega_0[k].copy() for k in range(K)}
+    Theta = {k: Omega_0[k].copy() for k in range(K)}
+    Lam = {k: Omega_0[k].copy() for k in range(K)}
+    L = {k: np.zeros((p[k], p[k])) for k in range(K)}
+    X0 = {k: np.zeros((p[k], p[k])) for k in range(K)} if X0 is None else {k: X0[k].copy() for k in range(K)}
+    X1 = {k: np.zeros((p[k], p[k])) for k in range(K)} if X1 is None else {k: X1[k].copy() for k in range(K)}
+    residual = np.zeros(max_iter)
+    status = ""
+    dim = ((p ** 2 + p) / 2).sum()
+    r = s = e_pri = e_dual = np.nan
+    for it in range(max_iter):
+        Omega_prev = {k: Omega[k].copy() for k in range(K)}
+        for k in range(K):
+            W = Theta[k] - L[k] - X0[k] - (1 / rho) * S[k]
+            D, Q = np.linalg.eigh(W)
+            Omega[k] = phiplus(1 / rho, D, Q)
+        for k in range(K):
+            V = (Omega[k] + L[k] + X0[k] + Lam[k] - X1[k]) * 0.5
+            Theta[k] = prox_od_1norm(V, lam1[k] / (2 * rho))
+        if latent:
+            for k in range(K):
+                C = Theta[k] - X0[k] - Omega[k]
+                C = (C.T + C) / 2
+                D, Q = np.linalg.eigh(C)
+                L[k] = prox_rank_norm(D, Q, mu[k] / rho)
+        Lam_prev = Lam
+        Lam = prox_2norm_G({k: Theta[k] + X1[k] for k in range(K)}, G, lambda2 / rho)
+        for k in range(K):
+            X0[k] = X0[k] + (Omega[k] - Theta[k] + L[k])
+            X1[k] = X1[k] + (Theta[k] - Lam[k])
+        if stopping_criterion == "boyd":
+            nr = np.linalg.norm
+            D1 = np.sqrt(sum(nr(Omega[k]) ** 2 + nr(Lam[k]) ** 2 for k in range(K)))
+            D2 = np.sqrt(sum(nr(Theta[k] - L[k]) ** 2 + nr(Theta[k]) ** 2 for k in range(K)))
+            D3 = np.sqrt(sum(nr(X0[k]) ** 2 + nr(X1[k]) ** 2 for k in range(K)))
+            e_pri = dim * tol + rtol * max(D1, D2)
+            e_dual = dim * tol + rtol * rho * D3
+            r = np.sqrt(sum(nr(Omega[k] - Theta[k] + L[k]) ** 2 + nr(Lam[k] - Theta[k]) ** 2 for k in range(K)))
+            s = rho * np.sqrt(sum(nr(Omega[k] - Omega_prev[k]) ** 2 + nr(Lam[k] - Lam_prev[k]) ** 2 for k in range(K)))
+            residual[it] = max(r, s)
+            if r <= e_pri and s <= e_dual:
+                status = "optimal"
+                break
+        else:
+            eta = _ext_kkt(Omega, Theta, L, Lam, {k: rho * X0[k] for k in range(K)}, {k: rho * X1[k] for k in range(K)},
+                           S, G, lam1, lambda2, latent, mu if latent else None)
+            residual[it] = eta
+            if eta <= tol:
+                status = "optimal"
+                break
+    status = _final_status(status, stopping_criterion, r, s, e_pri, e_dual)
+    sol = {"Omega": Omega, "Theta": Theta, "L": L, "X0": X0, "X1": X1}
+    return sol, {"status": status, "iterations": it + 1, "residual": residual[:it + 1]}
+
+
+def _ext_kkt(Omega, Theta, L, Lam, X0, X1, S, G, lam1, lambda2, latent, mu):
+    K = len(S)
+    nr = np.linalg.norm
+    t = np.zeros((6, K))
+    for k in range(K):
+        D, Q = np.linalg.eigh(Omega[k] - S[k] - X0[k])
+        t[0, k] = nr(Omega[k] - phiplus(1, D, Q)) / (1 + nr(Omega[k]))
+        t[1, k] = nr(Theta[k] - prox_od_1norm(Theta[k] + X0[k] - X1[k], lam1[k])) / (1 + nr(Theta[k]))
+        if latent:
+            D, Q = np.linalg.eigh(L[k] - X0[k])
+            t[2, k] = nr(L[k] - prox_rank_norm(D, Q, mu[k])) / (1 + nr(L[k]))
+        t[4, k] = nr(Omega[k] - Theta[k] + L[k]) / (1 + nr(Theta[k]))
+        t[5, k] = nr(Lam[k] - Theta[k]) / (1 + nr(Theta[k]))
+    V = prox_2norm_G({k: Lam[k] + X1[k] for k in range(K)}, G, lambda2)
+    for k in range(K):
+        t[3, k] = nr(V[k] - Lam[k]) / (1 + nr(Lam[k]))
+    return max(nr(t[i]) for i in range(6))

@@ -189,9 +189,51 @@ def fsgl_fixtures():
     save("fsgl_p12_M3", **out)
 
 
+def ext_fixtures():
+    """non-conforming GGL (src/gglasso/solver/ext_admm_solver.py): three instances sharing part of their variables;
+    the bookkeeping array G is built with the reference's own helpers (helper/ext_admm_helper.py)."""
+    import pandas as pd
+    import gglasso.solver.ext_admm_solver as ref_e
+    from gglasso.helper.ext_admm_helper import construct_indexer, create_group_array, check_G, construct_trivial_G
+    rng = np.random.default_rng(2024)
+    all_vars = np.arange(18)
+    subsets = [np.arange(0, 12), np.arange(4, 18), np.r_[0:6, 10:16]]
+    N = 300
+    Aall = rng.standard_normal((18, 18)) * (rng.random((18, 18)) < 0.15)
+    Prec = Aall @ Aall.T * 0.4 + np.eye(18)
+    Sig = np.linalg.inv(Prec)
+    samples, S = [], {}
+    for k, idx in enumerate(subsets):
+        X = rng.multivariate_normal(np.zeros(len(idx)), Sig[np.ix_(idx, idx)], N).T
+        samples.append(pd.DataFrame(X, index=idx))
+        S[k] = np.cov(X, bias=True)
+    ix_exist, ix_location = construct_indexer(samples)
+    G = quiet(create_group_array, ix_exist, ix_location)
+    p = np.array([len(s) for s in subsets])
+    check_G(G, p)
+    Om0 = {k: np.eye(p[k]) for k in range(3)}
+    out = dict(G=G, p=p, lambda1=0.05, lambda2=0.08)
+    for k in range(3):
+        out[f"S{k}"] = S[k]
+    for tag, kw in (("boyd", dict(tol=1e-7, rtol=1e-7)), ("latent", dict(tol=1e-7, rtol=1e-7, latent=True, mu1=0.3)),
+                    ("kkt", dict(tol=1e-4, stopping_criterion="kkt", max_iter=400))):
+        sol, info = quiet(ref_e.ext_ADMM_MGL, S, 0.05, 0.08, "GGL", Om0, G, measure=True, **kw)
+        out[f"status_{tag}"] = info["status"]
+        out[f"residual_{tag}"] = info["residual"]
+        for name in ("Omega", "Theta", "L", "X0", "X1"):
+            for k in range(3):
+                out[f"{name}{k}_{tag}"] = sol[name][k]
+    # trivial G (conforming) for the consistency check with ADMM_MGL (tests/test_solvers.py:71-120)
+    out["G_trivial"] = construct_trivial_G(12, 3)
+    save("ext_mgl_K3", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "fsgl":
         fsgl_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ext":
+        ext_fixtures()
     else:
         main()
         fsgl_fixtures()
+        ext_fixtures()

@@ -575,3 +575,48 @@ def test_eigh_large_odd_sizes(M, p):
     for m in range(M):
         assert np.abs(Q[m].T @ Q[m] - np.eye(p)).max() < 1e-12
         assert np.abs(A[m] @ Q[m] - Q[m] * D[m]).max() < 1e-11
+
+
+EXT_CASES = [("boyd", dict(tol=1e-7, rtol=1e-7)), ("latent", dict(tol=1e-7, rtol=1e-7, latent=True, mu1=0.3)),
+             ("kkt", dict(tol=1e-4, stopping_criterion="kkt", max_iter=400))]
+
+
+@pytest.mark.parametrize("tag,kw", EXT_CASES)
+def test_ext_admm_mgl_vs_reference_golden(golden, tag, kw):
+    """non-conforming group graphical lasso (three instances of size 12/14/12 sharing variables) vs the reference."""
+    from gglasso_b200 import ext_ADMM_MGL
+    g = golden("ext_mgl_K3")
+    p = g["p"]
+    S = {k: g[f"S{k}"] for k in range(3)}
+    Om0 = {k: np.eye(int(p[k])) for k in range(3)}
+    (sol, info), out = _quiet(ext_ADMM_MGL, S, float(g["lambda1"]), float(g["lambda2"]), "GGL", Om0, g["G"],
+                              measure=True, **kw)
+    n = len(g[f"residual_{tag}"])
+    assert info["status"] == str(g[f"status_{tag}"]) and len(info["residual"]) == n
+    assert f"ADMM terminated after {n} iterations" in out
+    np.testing.assert_allclose(info["residual"], g[f"residual_{tag}"], rtol=1e-6, atol=1e-12)
+    assert set(sol) == {"Omega", "Theta", "L", "X0", "X1"}
+    for name in sol:
+        for k in range(3):
+            ref = g[f"{name}{k}_{tag}"]
+            assert sol[name][k].shape == ref.shape
+            assert np.linalg.norm(sol[name][k] - ref) <= PER_ITER_TOL * max(1.0, np.linalg.norm(ref)), (name, k)
+    for k in range(3):
+        assert np.array_equal(sol["Theta"][k] != 0, g[f"Theta{k}_{tag}"] != 0)
+
+
+def test_ext_admm_consistent_with_conforming_solver(golden):
+    """reference tests/test_solvers.py:71-120: with all variables in all instances (trivial G) and lambda2/sqrt(K)
+    the extended solver solves the same problem as ADMM_MGL."""
+    from gglasso_b200 import ADMM_MGL, ext_ADMM_MGL
+    g = golden("ext_mgl_K3")
+    G = g["G_trivial"]
+    rng = np.random.default_rng(7)
+    K, p = 3, 12
+    S = np.stack([np.cov(rng.standard_normal((p, 200)), bias=True) for _ in range(K)])
+    Sd = {k: S[k].copy() for k in range(K)}
+    Om0 = {k: np.eye(p) for k in range(K)}
+    (se, _), _ = _quiet(ext_ADMM_MGL, Sd, 0.05, 0.02 / np.sqrt(K), "GGL", Om0, G, tol=1e-9, rtol=1e-9)
+    (sm, _), _ = _quiet(ADMM_MGL, S, 0.05, 0.02, "GGL", np.repeat(np.eye(p)[None], K, 0), tol=1e-9, rtol=1e-9)
+    for k in range(K):
+        assert np.abs(se["Theta"][k] - sm["Theta"][k]).max() < 1e-4

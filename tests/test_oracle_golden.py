@@ -152,3 +152,30 @@ def test_fsgl_matches_reference(golden):
             assert np.linalg.norm(sol[k] - g[f"{k}_{tag}"]) <= RTOL * max(1.0, np.linalg.norm(g[f"{k}_{tag}"])), k
         assert np.array_equal(sol["Theta"] != 0, g[f"Theta_{tag}"] != 0)
     assert np.linalg.norm(sol["L"] - g["L_lat"]) <= RTOL * max(1.0, np.linalg.norm(g["L_lat"]))
+
+
+def _ext_inputs(g):
+    p = g["p"]
+    S = {k: g[f"S{k}"] for k in range(len(p))}
+    Om0 = {k: np.eye(int(p[k])) for k in range(len(p))}
+    return S, Om0, g["G"], float(g["lambda1"]), float(g["lambda2"])
+
+
+EXT_CASES = [("boyd", dict(tol=1e-7, rtol=1e-7)), ("latent", dict(tol=1e-7, rtol=1e-7, latent=True, mu1=0.3)),
+             ("kkt", dict(tol=1e-4, stopping_criterion="kkt", max_iter=400))]
+
+
+@pytest.mark.parametrize("tag,kw", EXT_CASES)
+def test_ext_admm_matches_reference(golden, tag, kw):
+    g = golden("ext_mgl_K3")
+    S, Om0, G, l1, l2 = _ext_inputs(g)
+    sol, info = orc.ext_admm_mgl(S, l1, l2, Om0, G, **kw)
+    assert info["status"] == str(g[f"status_{tag}"])
+    assert len(info["residual"]) == len(g[f"residual_{tag}"])
+    np.testing.assert_allclose(info["residual"], g[f"residual_{tag}"], rtol=1e-6, atol=1e-13)
+    for name in ("Omega", "Theta", "L", "X0", "X1"):
+        for k in range(3):
+            ref = g[f"{name}{k}_{tag}"]
+            assert np.linalg.norm(sol[name][k] - ref) <= RTOL * max(1.0, np.linalg.norm(ref)), (name, k)
+    for k in range(3):
+        assert np.array_equal(sol["Theta"][k] != 0, g[f"Theta{k}_{tag}"] != 0)
