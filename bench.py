@@ -29,7 +29,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -46,33 +45,38 @@ def make_input(cfg):
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """samples nvidia-smi clocks / throttle reasons during the timed region: ONE long-running `nvidia-smi -lms 200`
+    process (started before, killed after) -- no per-sample fork that could stall the launching thread."""
 
     def __init__(self, idx):
-        self.idx, self.rows, self.stop = idx, [], False
-        self.t = threading.Thread(target=self.run, daemon=True)
+        self.idx, self.rows, self.proc = idx, [], None
 
-    def run(self):
+    def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self.stop:
-            try:
-                o = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
-
-    def __enter__(self):
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
 
     def summary(self):
         if not self.rows:
@@ -148,6 +152,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.load()
+    import gglasso_b200._engine as _eng
+    _eng.warmup()                              # one-time process init (pinned staging buffers), outside timed regions
     cfg = dict(CFG)
     cfg["seed"] = CFG["seed"] + rank          # each rank: its own replica of the workload
     S = make_input(cfg)
@@ -203,17 +209,20 @@ def main():
     roof = kernel_roofline(st, sweeps, ms / steps) if rank == 0 else None
 
     # ---------------- end to end through the public API (host buffers) ---------------------------
-    barrier()
-    t0 = time.perf_counter()
-    with contextlib.redirect_stdout(io.StringIO()):
-        if world == 1:
-            sol, info = ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=0.0, rtol=0.0, max_iter=steps)
-        else:
-            sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K * world,
-                                      tol=0.0, rtol=0.0, max_iter=steps, check_every=10 ** 9)
-            sol.pop("L")
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = None
+    for rep in range(2):          # first call = warm-up (lazy kernel module loading, allocator); second is reported
+        barrier()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            if world == 1:
+                sol, info = ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=0.0, rtol=0.0,
+                                     max_iter=steps)
+            else:
+                sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K * world,
+                                          tol=0.0, rtol=0.0, max_iter=steps, check_every=10 ** 9)
+                sol.pop("L")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

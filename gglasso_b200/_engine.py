@@ -43,10 +43,43 @@ def to_dev(a, dev):
     if isinstance(a, torch.Tensor):
         return a.to(device=dev, dtype=torch.float64, copy=True).contiguous()
     a = np.ascontiguousarray(a, dtype=np.float64)
-    return torch.from_numpy(a).to(dev, non_blocking=False)
+    if a.nbytes < (8 << 20):
+        return torch.from_numpy(a).to(dev, non_blocking=False)
+    # large inputs: host memcpy into two pinned staging buffers overlapped with async H2D of the previous chunk
+    bufs, evs = _staging()
+    ce = bufs[0].numel()
+    out = torch.empty(a.shape, dtype=torch.float64, device=dev)
+    src = torch.from_numpy(a).view(-1)
+    dst = out.view(-1)
+    n = src.numel()
+    for i, lo in enumerate(range(0, n, ce)):
+        hi = min(n, lo + ce)
+        b = bufs[i & 1]
+        evs[i & 1].synchronize()                       # previous H2D out of this buffer has finished
+        b[:hi - lo].copy_(src[lo:hi])
+        dst[lo:hi].copy_(b[:hi - lo], non_blocking=True)
+        evs[i & 1].record()
+    torch.cuda.current_stream().synchronize()
+    return out
 
 
 _STAGE = {}
+
+
+def _staging(chunk_bytes=32 << 20):
+    if "bufs" not in _STAGE:
+        _STAGE["bufs"] = [torch.empty(chunk_bytes // 8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        _STAGE["evs"] = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in _STAGE["evs"]:
+            ev.record()
+    return _STAGE["bufs"], _STAGE["evs"]
+
+
+def warmup():
+    """one-time process initialisation (library load, pinned staging buffers); optional."""
+    _lib.load()
+    require_cuda()
+    _staging()
 
 
 def to_host(t, chunk_bytes=32 << 20):
@@ -58,11 +91,8 @@ def to_host(t, chunk_bytes=32 << 20):
     if n * 8 <= (1 << 20):
         out[...] = t.cpu().numpy()
         return out
-    ce = chunk_bytes // 8
-    if "bufs" not in _STAGE:
-        _STAGE["bufs"] = [torch.empty(ce, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        _STAGE["evs"] = [torch.cuda.Event(), torch.cuda.Event()]
-    bufs, evs = _STAGE["bufs"], _STAGE["evs"]
+    bufs, evs = _staging(chunk_bytes)
+    ce = bufs[0].numel()
     src = t.view(-1)
     dst = torch.from_numpy(out).view(-1)
     nchunks = (n + ce - 1) // ce
@@ -214,6 +244,66 @@ class AdmmState:
         _lib.check(self.lib.gg_asym_max(_p(A), self.M, self.p, _p(out), self.stream), "gg_asym_max")
         return float(out.max().item())
 
+    def is_posdef(self, A, res=None):
+        """PD check of the reference (eigvalsh(Theta - L).min() > 0, admm_solver.py:294-296) without an extra
+        eigendecomposition whenever a certificate is available:
+          (1) Weyl: lambda_min(Theta-L) >= lambda_min(Omega) - |Omega-Theta+L|_F, with lambda_min(Omega) =
+              phi+(min d) from the eigenvalues of the last Omega step (still resident) and the norm = the final
+              primal residual r -- available for the non-latent 'boyd' loop;
+          (2) a positive Gershgorin lower bound;
+        otherwise the exact smallest eigenvalue is computed (min_eig)."""
+        if res is not None and not self.latent and res.get("D_is_W") and self.nprob == 1:
+            n = int(res["iters"][0])
+            r, rho_used = res["hist"][0, n - 1, 0], res["hist"][0, n - 1, 4]
+            beta = (self.nk if self.nk is not None else torch.ones(self.M, dtype=torch.float64, device=self.dev)) / rho_used
+            dmin = self.eig.D.min(dim=1).values
+            lam_min_omega = 0.5 * (torch.sqrt(dmin * dmin + 4 * beta) + dmin)
+            if float(lam_min_omega.min().item()) - float(r) > 0.0:
+                return True, None
+        out = torch.empty(self.M, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.gg_gershgorin_min(_p(A), self.M, self.p, _p(self.eig.ws), self.eig.ws_bytes, _p(out),
+                                              self.stream), "gg_gershgorin_min")
+        if float(out.min().item()) > 0.0:
+            return True, None
+        d = self.min_eig(A)
+        return d > 0, d
+
+    def posdef_async(self, A, res=None):
+        """like is_posdef, but when an eigendecomposition is needed it is only ENQUEUED (tridiagonal path: no host
+        synchronisation) and a device scalar is returned, so the caller can overlap it with the D2H copies of the
+        solution.  Returns None (certified PD) or a 0-d device tensor holding the smallest eigenvalue."""
+        if res is not None and not self.latent and res.get("D_is_W") and self.nprob == 1:
+            n = int(res["iters"][0])
+            r, rho_used = res["hist"][0, n - 1, 0], res["hist"][0, n - 1, 4]
+            beta = (self.nk if self.nk is not None else torch.ones(self.M, dtype=torch.float64, device=self.dev)) / rho_used
+            dmin = self.eig.D.min(dim=1).values
+            lam_min_omega = 0.5 * (torch.sqrt(dmin * dmin + 4 * beta) + dmin)
+            if float(lam_min_omega.min().item()) - float(r) > 0.0:
+                return None
+        B = A.clone()
+        D = self.eig.eigh(B, ctrl=None, mpp=1, vectors=0, stream=self.stream)
+        return D.min()
+
+    def mark(self):
+        """event on the main stream: everything enqueued so far (the ADMM loop) -- used as the dependency of the
+        overlapped D2H so that it does not wait for work enqueued later (the PD-check eigendecomposition)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def to_host_overlapped(self, tensors, after=None):
+        """D2H of the solution arrays on a side stream (copy engine) while the main stream keeps computing."""
+        side = getattr(self, "_side", None)
+        if side is None:
+            side = self._side = torch.cuda.Stream(device=self.dev)
+        if after is not None:
+            side.wait_event(after)
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            out = [to_host(t) for t in tensors]
+        return out
+
     def min_eig(self, A):
         """smallest eigenvalue over the stack (post-loop PD checks; reference uses eigvalsh)."""
         B = A.clone()
@@ -362,6 +452,8 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
         info["residual"] = [kkt_res[:it_done]] * nprob
     info["runtime"] = runtime
     info["objective"] = objective
+    # st.eig.D still holds the eigenvalues of the last W (not overwritten by objective / KKT evaluations)
+    info["D_is_W"] = (stopping_criterion == "boyd") and not measure and not latent
     return st, info
 
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "gg_objective_nparts": (_i, [_i]),
     "gg_objective": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_asym_max": (_i, [_vp, _i, _i, _vp, _vp]),
+    "gg_gershgorin_min": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "gg_host_tv1d": (None, [ctypes.POINTER(_d), _i, _i, _d]),
 }
 

@@ -33,6 +33,7 @@ int gg_launch_ext_dual(double*, double*, const double*, const double*, const dou
                        const double*, const double*, const int*, int, int, double*, cudaStream_t);
 int gg_launch_prox_band(const double*, double*, const double*, double, double, int, int, int, int, int, cudaStream_t);
 size_t gg_tridiag_ws_bytes(int, int);
+int gg_gershgorin_min_impl(const double*, int, int, void*, size_t, double*, cudaStream_t);
 
 extern "C" {
 
@@ -166,6 +167,12 @@ int gg_ext_dual(double* X0, double* X1, const double* Omega, const double* Omega
     if (K <= 0 || p <= 0) return -1;
     return gg_launch_ext_dual(X0, X1, Omega, Omega_prev, Theta, L, Lam, Lam_prev, ctrl, pvec, K, p, partials,
                               (cudaStream_t)stream);
+}
+
+int gg_gershgorin_min(const double* A, int M, int p, void* ws, size_t ws_bytes, double* out, void* stream)
+{
+    if (M <= 0 || p <= 0) return -1;
+    return gg_gershgorin_min_impl(A, M, p, ws, ws_bytes, out, (cudaStream_t)stream);
 }
 
 void gg_host_tv1d(double* v, int n, int stride, double lam) { gg_tv1d_inplace(v, n, stride, lam); }

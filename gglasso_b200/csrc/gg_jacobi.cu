@@ -540,3 +540,30 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
     if (info) info[0] = used;
     return 0;
 }
+
+// Gershgorin lower bound of the spectrum per matrix: out[m] = min_i (a_ii - sum_{j != i} |a_ij|).
+// A positive value proves positive definiteness, so the post-loop PD check (admm_solver.py:294-296) can skip
+// its eigendecomposition.
+__global__ void __launch_bounds__(256)
+gersh_min_kernel(const double* __restrict__ rowlo, int p, double* __restrict__ out)
+{
+    __shared__ double red[32];
+    const int m = blockIdx.x;
+    double lo = 1.0e300;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) lo = fmin(lo, rowlo[(size_t)m * p + i]);
+    const double nlo = gg_block_max(-lo, red);
+    if (threadIdx.x == 0) out[m] = -nlo;
+}
+
+int gg_gershgorin_min_impl(const double* A, int M, int p, void* ws, size_t ws_bytes, double* out, cudaStream_t s)
+{
+    if (ws_bytes < 2 * align_up(sizeof(double) * (size_t)M * p, 256)) return -3;
+    double* rowlo = (double*)ws;
+    double* rowhi = (double*)((char*)ws + align_up(sizeof(double) * (size_t)M * p, 256));
+    dim3 grows((p + 7) / 8, M);
+    gersh_rows_kernel<<<grows, 256, 0, s>>>(A, p, rowlo, rowhi);
+    GG_CHECK_LAUNCH();
+    gersh_min_kernel<<<M, 256, 0, s>>>(rowlo, p, out);
+    GG_CHECK_LAUNCH();
+    return 0;
+}

@@ -95,16 +95,19 @@ def ADMM_MGL(S: np.ndarray,
         if dev_max > 1e-5:
             warnings.warn(f"{name} variable is not symmetric, largest deviation is {dev_max}.")
 
-    ### CHECK FOR POSDEF
+    ### CHECK FOR POSDEF (eigenvalue computations are enqueued first and overlap the D2H copies of the solution)
     TL = st.Theta - st.L if latent else st.Theta
-    if st.min_eig(TL) <= 0:
+    loop_done = st.mark()
+    pd_min = st.posdef_async(TL, res)
+    psd_min = st.posdef_async(st.L) if latent else None
+    outs = st.to_host_overlapped([Omega_d, st.Theta, st.X] + ([st.L] if latent else []), after=loop_done)
+    if pd_min is not None and float(pd_min.item()) <= 0:
         print("WARNING: Theta (Theta - L resp.) is not positive definite. Solve to higher accuracy!")
     if latent:
-        if st.min_eig(st.L) < -1e-5:
+        if float(psd_min.item()) < -1e-5:
             print("WARNING: L is not positive semidefinite. Solve to higher accuracy!")
 
-    sol = {'Omega': to_host(Omega_d), 'Theta': to_host(st.Theta),
-           'L': to_host(st.L) if latent else np.zeros((K, p, p)), 'X': to_host(st.X)}
+    sol = {'Omega': outs[0], 'Theta': outs[1], 'L': outs[3] if latent else np.zeros((K, p, p)), 'X': outs[2]}
     if measure:
         info = {'status': status,
                 'runtime': res["runtime"][:n_it],

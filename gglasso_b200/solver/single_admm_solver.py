@@ -83,8 +83,8 @@ def ADMM_SGL(S: np.ndarray,
 
     ### CHECK FOR POSDEF
     TL = st.Theta - st.L if latent else st.Theta
-    dmin = st.min_eig(TL)
-    if dmin <= 0:
+    ok, dmin = st.is_posdef(TL, res)
+    if not ok:
         print(f"WARNING: Theta (Theta - L resp.) is not positive definite. Solve to higher accuracy! (min EV is {dmin})")
     if latent:
         dmin = st.min_eig(st.L)

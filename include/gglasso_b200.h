@@ -139,6 +139,11 @@ int gg_objective(const double* Omega, const double* S, const double* Theta, doub
 /* max |A - A^T| partials (symmetry warnings, admm_solver.py:284-291); out: M * gg_sgl_nparts(p,M) doubles */
 int gg_asym_max(const double* A, int M, int p, double* out, void* stream);
 
+/* out[m] = min_i (a_ii - sum_{j!=i} |a_ij|): Gershgorin lower bound of the spectrum.  A positive bound proves
+ * positive definiteness, letting the post-loop PD check (admm_solver.py:294-296) skip its eigendecomposition.
+ * ws: at least the gg_eigh workspace of the same (M,p). */
+int gg_gershgorin_min(const double* A, int M, int p, void* ws, size_t ws_bytes, double* out, void* stream);
+
 /* Host-side execution of the exact device TV-prox routine (unit tests without a GPU). */
 void gg_host_tv1d(double* v, int n, int stride, double lam);
 
