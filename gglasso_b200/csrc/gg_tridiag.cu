@@ -127,10 +127,14 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restr
 {
     __shared__ double tile[SV_T][SV_T + 1];
     __shared__ double s_vpI[SV_T], s_wI[SV_T], s_vI[SV_T], s_vpJ[SV_T], s_wJ[SV_T], s_vJ[SV_T];
-    const int m = blockIdx.y;
+    // Boustrophedon sweep: consecutive launches walk the (matrix, tile) space in opposite directions, so a launch
+    // starts with the tiles the previous one touched last -- they are still in L2 (an identical sweep order is the
+    // worst case for an LRU-like cache when the ~80 MB working set exceeds the usable capacity).
+    const bool rev = (j & 1) != 0;
+    const int m = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     const int t = n - j - 1;
     const int base = j + 1;
-    int idx = blockIdx.x, I = 0;
+    int idx = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, I = 0;
     while (idx >= nt - I) { idx -= nt - I; ++I; }
     const int J = I + idx;
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
@@ -598,9 +602,9 @@ dc_secular_kernel(int n, int level, double* __restrict__ lam_out, DcWs ws, const
         for (int it = 0; it < 100; ++it) {
             double psi = 0.0, phi = 0.0, dpsi = 0.0, dphi = 0.0, sabs = 0.0;
             for (int i = lane; i < k; i += 32) {
-                const double dlt = (sdl[i] - dorg) - tau;
-                const double t = sw2[i] / dlt;
-                const double dt = t / dlt;
+                const double rcp = 1.0 / ((sdl[i] - dorg) - tau);      // one division per term
+                const double t = sw2[i] * rcp;
+                const double dt = t * rcp;
                 if (i < split) { psi += t; dpsi += dt; } else { phi += t; dphi += dt; }
                 sabs += fabs(t);
             }
@@ -653,19 +657,23 @@ dc_zhat_kernel(int n, int level, DcWs ws, const int* __restrict__ skip)
     const double* Dm = ws.U + (size_t)m * n * n + (size_t)lo * n + lo;
     const double di = dl[i];
     // four independent partial products: the FP64 divisions are latency bound, not throughput bound
-    double pr[4] = {Dm[(size_t)i * n + i], 1.0, 1.0, 1.0};
+    // numerators and denominators are multiplied up in chunks of 8 terms (each factor lies in [1e-16, 4] after the
+    // normalisation of T, so a chunk cannot over/underflow) and divided once per chunk: 8x fewer FP64 divisions
+    double prod = Dm[(size_t)i * n + i];
     int j = 0;
-    for (; j + 4 <= k; j += 4) {
+    for (; j + 8 <= k; j += 8) {
+        double num = 1.0, den = 1.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int jj = j + u;
-            const double num = Dm[(size_t)jj * n + i], den = di - dl[jj];
-            pr[u] *= (jj != i) ? num / den : 1.0;
+            const bool self = (jj == i);
+            num *= self ? 1.0 : Dm[(size_t)jj * n + i];
+            den *= self ? 1.0 : (di - dl[jj]);
         }
+        prod *= num / den;
     }
     for (; j < k; ++j)
-        if (j != i) pr[0] *= Dm[(size_t)j * n + i] / (di - dl[j]);
-    const double prod = (pr[0] * pr[1]) * (pr[2] * pr[3]);
+        if (j != i) prod *= Dm[(size_t)j * n + i] / (di - dl[j]);
     ws.zhat[(size_t)m * n + lo + i] = copysign(sqrt(-prod), ws.wnd[(size_t)m * n + lo + i]);
 }
 
