@@ -184,21 +184,30 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restr
     for (int q = 0; q < 16; ++q) tile[rq + 4 * q][cl] = a[q];
     __syncthreads();
     double* y = ws.y + (size_t)m * n + base;
+    // four independent accumulators per sum: the 64-term FMA chains are latency bound in the small-t regime
     if (tid < SV_T) {                                  // row sums -> y_I (includes the diagonal)
-        double s = 0.0;
-#pragma unroll 8
-        for (int cc = 0; cc < SV_T; ++cc) s = fma(tile[tid][cc], s_vJ[cc], s);
-        if (r0 + tid < t) atomicAdd(y + r0 + tid, s);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+        for (int cc = 0; cc < SV_T; cc += 4) {
+            s0 = fma(tile[tid][cc], s_vJ[cc], s0);
+            s1 = fma(tile[tid][cc + 1], s_vJ[cc + 1], s1);
+            s2 = fma(tile[tid][cc + 2], s_vJ[cc + 2], s2);
+            s3 = fma(tile[tid][cc + 3], s_vJ[cc + 3], s3);
+        }
+        if (r0 + tid < t) atomicAdd(y + r0 + tid, (s0 + s1) + (s2 + s3));
     } else if (tid < 2 * SV_T) {                       // column sums -> y_J (strictly upper part only)
         const int cc = tid - SV_T;
-        double s = 0.0;
-        if (I == J) {
-            for (int rr = 0; rr < cc; ++rr) s = fma(tile[rr][cc], s_vI[rr], s);
-        } else {
-#pragma unroll 8
-            for (int rr = 0; rr < SV_T; ++rr) s = fma(tile[rr][cc], s_vI[rr], s);
+        const int rend = (I == J) ? cc : SV_T;         // diagonal tile: rows above the diagonal only
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int rr = 0;
+        for (; rr + 4 <= rend; rr += 4) {
+            s0 = fma(tile[rr][cc], s_vI[rr], s0);
+            s1 = fma(tile[rr + 1][cc], s_vI[rr + 1], s1);
+            s2 = fma(tile[rr + 2][cc], s_vI[rr + 2], s2);
+            s3 = fma(tile[rr + 3][cc], s_vI[rr + 3], s3);
         }
-        if (c0 + cc < t) atomicAdd(y + c0 + cc, s);
+        for (; rr < rend; ++rr) s0 = fma(tile[rr][cc], s_vI[rr], s0);
+        if (c0 + cc < t) atomicAdd(y + c0 + cc, (s0 + s1) + (s2 + s3));
     }
 }
 
