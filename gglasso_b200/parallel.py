@@ -258,11 +258,14 @@ def _score_device(st, Omega_unused, N, gamma, method):
 
 
 def grid_search_device(S, N, reg, l1, l2, method="eBIC", gamma=0.1, tol=1e-7, rtol=1e-7, latent=False, mu1=None,
-                       group=None):
+                       group=None, n_streams=1):
     """lambda1 x lambda2 grid with everything resident on the GPU: S is uploaded once, each grid point runs the
     device ADMM loop, is scored on the device (eBIC/AIC) and hands its Omega to the next point of the column as
     warm start without touching the host; only the winning solution is copied back.  Columns (lambda1 values) are
     dealt round-robin to the ranks of ``group`` (one process per GPU); see grid_search_dist for the semantics.
+
+    ``n_streams`` > 1 additionally runs that many columns concurrently on this GPU (one worker thread and CUDA
+    stream each) -- worthwhile when a single solve cannot fill the device (p of a few hundred).
 
     Returns (scores (len(l2), len(l1)), iterations (same shape), best_index (g1, g2), best_sol) on every rank.
     """
@@ -282,19 +285,54 @@ def grid_search_device(S, N, reg, l1, l2, method="eBIC", gamma=0.1, tol=1e-7, rt
     mu = None
     if latent:
         mu = mu1 * np.ones(K) if np.isscalar(mu1) else np.asarray(mu1, dtype=np.float64)
-    for g2 in range(rank, len(l1), world):
-        Omega_0 = eye
-        for g1 in range(len(l2)):
-            st, res = run_admm("mgl", S_dev, Omega_0, None, None, lambda1=float(l1[g2]), lambda2=float(l2[g1]),
-                               reg=reg, tol=tol, rtol=rtol, latent=latent, mu=mu)
-            n = int(res["iters"][0])
-            Omega_0 = st.final_omega(res["iters"])
-            sc = _score_device(st, Omega_0, N, gamma, method)
-            scores[g1, g2], iters[g1, g2] = sc, n
-            if sc < best_score:
-                best_score, best_ix = sc, (g1, g2)
-                best = {"Omega": Omega_0.clone(), "Theta": st.Theta.clone(), "X": st.X.clone(),
-                        "L": st.L.clone() if latent else None}
+    my_cols = list(range(rank, len(l1), world))
+    n_streams = max(1, min(int(n_streams), len(my_cols))) if my_cols else 1
+
+    def run_columns(cols, out):
+        """one worker = one CUDA stream: its columns run back to back, warm starts stay on the device"""
+        b, b_score, b_ix = None, np.inf, None
+        for g2 in cols:
+            Omega_0 = eye
+            for g1 in range(len(l2)):
+                st, res = run_admm("mgl", S_dev, Omega_0, None, None, lambda1=float(l1[g2]), lambda2=float(l2[g1]),
+                                   reg=reg, tol=tol, rtol=rtol, latent=latent, mu=mu)
+                n = int(res["iters"][0])
+                Omega_0 = st.final_omega(res["iters"])
+                sc = _score_device(st, Omega_0, N, gamma, method)
+                scores[g1, g2], iters[g1, g2] = sc, n
+                if sc < b_score:
+                    b_score, b_ix = sc, (g1, g2)
+                    b = {"Omega": Omega_0.clone(), "Theta": st.Theta.clone(), "X": st.X.clone(),
+                         "L": st.L.clone() if latent else None}
+        out.append((b_score, b_ix, b))
+
+    results = []
+    if n_streams == 1:
+        run_columns(my_cols, results)
+    else:
+        # the grid points of different columns are independent and, at these sizes, latency bound: several
+        # columns share the GPU from worker threads on their own streams (ctypes releases the GIL in the C calls)
+        import threading
+        torch.cuda.synchronize()
+        errs = []
+
+        def worker(cols):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                    run_columns(cols, results)
+                    torch.cuda.current_stream().synchronize()
+            except Exception as ex:                     # surface worker failures in the caller
+                errs.append(ex)
+
+        threads = [threading.Thread(target=worker, args=(my_cols[w::n_streams],)) for w in range(n_streams)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        if errs:
+            raise errs[0]
+    for b_score, b_ix, b in results:
+        if b is not None and b_score < best_score:
+            best_score, best_ix, best = b_score, b_ix, b
     if best is not None:
         best = {k: (to_host(v) if v is not None else np.zeros((K, p, p))) for k, v in best.items()}
     if world > 1:

@@ -61,6 +61,10 @@ l1 = np.logspace(0, -3, 10); l2 = np.logspace(-1, -4, 10)
 t, (scores, ix, best) = wall(lambda: grid_search_dist(ADMM_MGL, S, N, "GGL", l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7))
 d = dict(gpu_grid_s=t, best_ix=[int(ix[0]), int(ix[1])], best_lambda=[float(l1[ix[1]]), float(l2[ix[0]])], nan_scores=int(np.isnan(scores).sum()))
 td, (sc_dev, it_dev, ix_dev, _) = wall(lambda: grid_search_device(S, N, "GGL", l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7))
+for ns in (2, 5):
+    tn, (sc_n, it_n, ix_n, _) = wall(lambda: grid_search_device(S, N, "GGL", l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7, n_streams=ns))
+    d[f"gpu_grid_device_resident_{ns}streams_s"] = tn
+    d[f"streams{ns}_scores_rel"] = float(np.nanmax(np.abs(sc_n - sc_dev) / np.abs(sc_dev)))
 d.update(gpu_grid_device_resident_s=td, device_best_ix=[int(ix_dev[0]), int(ix_dev[1])], total_admm_iterations=int(it_dev.sum()),
          device_vs_host_scores_rel=float(np.nanmax(np.abs(sc_dev - scores) / np.abs(scores))))
 if not skip_cpu:

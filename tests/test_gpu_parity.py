@@ -503,6 +503,11 @@ def test_grid_search_device_resident_matches_host_driver():
         assert _rel(best_d[k], best_h[k]) < PER_ITER_TOL, k
     sc_a, _, _, _ = grid_search_device(S, np.full(K, N), "FGL", l1[:1], l2[:1], method="AIC")
     assert np.isfinite(sc_a).all()
+    # several columns concurrently on one GPU (worker threads + streams) must give the same table
+    sc_s, it_s, ix_s, best_s = grid_search_device(S, np.full(K, N), "GGL", l1, l2, gamma=0.1, n_streams=3)
+    np.testing.assert_allclose(sc_s, sc_d, rtol=1e-9)
+    assert tuple(ix_s) == tuple(ix_d) and np.array_equal(it_s, it_d)
+    assert _rel(best_s["Theta"], best_d["Theta"]) < PER_ITER_TOL
 
 
 def test_admm_fsgl_vs_reference_golden(golden):
