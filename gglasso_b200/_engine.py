@@ -182,7 +182,7 @@ class AdmmState:
         self.eig = Eigh(self.M, self.p, dev)
         # warm start of the small-matrix eigensolver: previous eigenvectors of W (and of C when latent)
         self.warm_w = self.warm_c = None
-        if self.p <= 160 and os.environ.get("GG_NO_WARM", "0") != "1":
+        if self.p <= 48 and os.environ.get("GG_NO_WARM", "0") != "1":
             eye = torch.eye(self.p, dtype=torch.float64, device=dev)
             self.warm_w = eye.repeat(self.M, 1, 1).contiguous()
             self.warm_c = self.warm_w.clone() if latent else None

@@ -39,7 +39,7 @@ extern "C" {
 
 int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_bytes, int which, void* stream)
 {
-    if (M <= 0 || p <= 160 || which < 0 || which > 2) return -1;
+    if (M <= 0 || p <= 32 || which < 0 || which > 2) return -1;
     if (ws_bytes < gg_tridiag_ws_bytes(M, p)) return -3;
     return gg_eigh_tridiag_impl(A, D, M, p, nullptr, 1, ws, ws_bytes, (cudaStream_t)stream, which == 0 ? 3 : which);
 }

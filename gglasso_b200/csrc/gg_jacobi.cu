@@ -17,8 +17,10 @@
 //                       eigenvectors U of H by the same shared-memory Jacobi, P <- U^T P by DMMA.
 #include "gg_common.cuh"
 #include "gg_jacobi_dev.cuh"
+#include <stdlib.h>
 
-#define GG_SMALL_MAX 160
+#define GG_SMALL_MAX 160            // largest matrix the shared-memory Jacobi kernel can hold
+#define GG_JACOBI_DEFAULT_MAX 48     // default crossover: above it the tridiagonal path is faster (p=100: 0.65 vs 1.86 ms)
 #define JS_THREADS 1024
 #define JS_LP 16
 
@@ -417,7 +419,7 @@ static size_t gg_jacobi_ws_bytes(int M, int p)
 size_t gg_eigh_ws_bytes(int M, int p)
 {
     const size_t a = gg_jacobi_ws_bytes(M, p);
-    const size_t b = (p > GG_SMALL_MAX) ? gg_tridiag_ws_bytes(M, p) : 0;
+    const size_t b = (p > 32) ? gg_tridiag_ws_bytes(M, p) : 0;
     return a > b ? a : b;
 }
 
@@ -465,7 +467,14 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
     if (tol <= 0.0) tol = fmax(1.0e-14, 8.0 * 2.220446049250313e-16 * sqrt((double)p));
     if (max_sweeps <= 0) max_sweeps = 30;
 
-    if (p <= GG_SMALL_MAX) {
+    static int small_max = -1;          // matrices up to this size use the shared-memory Jacobi kernel
+    if (small_max < 0) {
+        const char* ev = getenv("GG_JACOBI_MAX");
+        small_max = ev ? atoi(ev) : GG_JACOBI_DEFAULT_MAX;
+        if (small_max > GG_SMALL_MAX) small_max = GG_SMALL_MAX;
+        if (small_max < 32) small_max = 32;          // the D&C leaves need n > 32
+    }
+    if (p <= small_max || (block_nb2 == 1 && p <= GG_SMALL_MAX)) {       // block_nb2 == 1 forces this path
         const int ld = p | 1;
         const size_t smem = sizeof(double) * (size_t)p * ld;
         static bool attr = false;

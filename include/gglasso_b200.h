@@ -44,7 +44,9 @@ int gg_build_w(const double* Theta, const double* L, double* X, const double* S,
 /* Batched symmetric eigendecomposition (replaces np.linalg.eigh at admm_solver.py:181,199 and
  * single_admm_solver.py:164,174).  A (M,p,p) is overwritten by Vt: row c of Vt[m] is the unit
  * eigenvector belonging to D[m][c] (order and signs arbitrary).  vectors=0 skips normalisation
- * (eigenvalues only).  block_nb2 in {0,32,64,128}: rows per block pair of the large-p path (0 = default).
+ * (eigenvalues only).  Path selection: p <= 48 shared-memory Jacobi (one CTA per matrix), larger p Householder
+ * tridiagonalisation + divide & conquer + back-transformation.  block_nb2 = 0: default; 1: force the shared-memory
+ * Jacobi kernel (p <= 160); 32/64/128: block-Jacobi with that many rows per block pair (p > 160).
  * tol<=0, max_sweeps<=0: defaults.  quad_tol: a sweep whose largest measured off-diagonal cosine is
  * below quad_tol is taken as the last one (quadratic convergence); 0 disables.  info[0] (host) = sweeps.
  * Vt_warm (optional, (M,p,p), rows orthonormal; used for p <= 160): warm start from the eigenvectors of the

@@ -38,8 +38,9 @@ def _sym(rng, p, scale=1.0):
 # --------------------------------------------------------------------------------------------
 # eigensolver + spectral reconstruction
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("p,nb2", [(161, 32), (200, 64), (333, 32), (512, 128)])
+@pytest.mark.parametrize("p,nb2", [(161, 32), (200, 64), (333, 32), (512, 128), (100, 1), (160, 1), (49, 1)])
 def test_eigh_block_jacobi_path(p, nb2):
+    """non-default eigensolver paths: block Jacobi (nb2 = 32/64/128) and the forced shared-memory Jacobi (nb2 = 1)"""
     from gglasso_b200._engine import eigh
     rng = np.random.default_rng(p)
     A = np.stack([_sym(rng, p) for _ in range(2)])
