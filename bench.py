@@ -329,13 +329,21 @@ def kernel_roofline(st, sweeps, ms_per_step):
                 best = min(best, a.elapsed_time(b))
         times[which] = best
     n_launch = p - 1
-    # algorithmic bytes of launch j: read + write of the UPPER TRIANGLE of the t x t trailing block (t = p-j-1)
-    # of each of the M matrices: 16 * t(t+1)/2 bytes
-    total_bytes = sum(16.0 * M * (p - j - 1) * (p - j) / 2 for j in range(p - 1))
+    # algorithmic bytes of launch j: one read of the UPPER TRIANGLE of the t x t trailing block (t = p-j-1) of each
+    # of the M matrices, 8 * t(t+1)/2 bytes, plus the same again on the passes that store it (every q-th pass,
+    # q = gg_sytrd_write_depth(); same schedule as the host loop in gg_tridiag.cu)
+    q = int(lib.gg_sytrd_write_depth())
+    total_bytes, kb, n_write = 0.0, 0, 0
+    for j in range(p - 1):
+        write = (j - kb) >= q
+        total_bytes += (16.0 if write else 8.0) * M * (p - j - 1) * (p - j) / 2
+        if write:
+            kb, n_write = j, n_write + 1
     achieved = total_bytes / (times[2] * 1e-3) / 1e9            # GB/s over all symv launches of one eigh
     return {"bound": "hbm", "kernel": "tr_symv_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
             "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
-            "launches_per_step": n_launch, "avg_ms_per_launch": times[2] / n_launch,
+            "launches_per_step": n_launch, "write_depth": q, "write_passes": n_write,
+            "avg_ms_per_launch": times[2] / n_launch,
             "algorithmic_bytes_per_launch_avg": total_bytes / n_launch,
             "symv_ms_per_step": times[2], "col_kernels_ms_per_step": times[1], "sytrd_ms_per_step": times[0],
             "share_of_step": times[2] / ms_per_step,

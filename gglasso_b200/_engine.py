@@ -368,6 +368,12 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             torch.cuda.synchronize()
             t0 = time.time()
         st.omega_step()
+        if measure and kind == "mgl":
+            # log det Omega_k = sum_i log phi+(d_i, beta_k) from the eigenvalues of W that are resident right now
+            # (no extra eigendecomposition); tiny (K,p) reduction, kept on the device until the objective is formed
+            beta = (st.nk if st.nk is not None else torch.ones(M, dtype=torch.float64, device=st.dev)) / st.ctrl[0, C_RHO]
+            Dw = st.eig.D
+            logdet_dev = torch.log(0.5 * (torch.sqrt(Dw * Dw + 4 * beta[:, None]) + Dw)).sum()
         C = st.W if latent else None
         if kind == "mgl":
             _lib.check(lib.gg_prox_mgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
@@ -390,7 +396,7 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             torch.cuda.synchronize()
             runtime[it] = time.time() - t0
             if kind == "mgl":
-                objective[it] = _objective(st, st.Omega_new, lambda1, lambda2, regi)
+                objective[it] = _objective(st, st.Omega_new, lambda1, lambda2, regi, logdet_dev)
         it_done = it + 1
         if stopping_criterion == "boyd":
             _lib.check(lib.gg_stop_update(_p(partials), nparts, _p(st.ctrl), _p(st.hist), st.hist_cap, _p(st.pdim),
@@ -453,20 +459,18 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     info["runtime"] = runtime
     info["objective"] = objective
     # st.eig.D still holds the eigenvalues of the last W (not overwritten by objective / KKT evaluations)
-    info["D_is_W"] = (stopping_criterion == "boyd") and not measure and not latent
+    info["D_is_W"] = (stopping_criterion == "boyd") and not latent
     return st, info
 
 
-def _objective(st, Omega, lambda1, lambda2, regi):
-    """f(Omega,S) + P(Theta) (admm_solver.py:213); -log det from the eigenvalues already on the device."""
+def _objective(st, Omega, lambda1, lambda2, regi, logdet):
+    """f(Omega,S) + P(Theta) (admm_solver.py:213): <Omega,S> and P(Theta) from gg_objective, -log det from the
+    eigenvalues of the Omega step (``logdet``: device scalar)."""
     lib = st.lib
     n = lib.gg_objective_nparts(st.p)
     parts = torch.empty((n, 2), dtype=torch.float64, device=st.dev)
     _lib.check(lib.gg_objective(_p(Omega), _p(st.S), _p(st.Theta), lambda1, lambda2, regi, st.M, st.p, _p(parts),
                                 st.stream), "gg_objective")
-    B = Omega.clone()
-    D = st.eig.eigh(B, ctrl=None, mpp=1, vectors=0, stream=st.stream)
-    logdet = torch.log(D).sum()
     tot = parts.sum(0)
     return float((-logdet + tot[0] + tot[1]).item())
 

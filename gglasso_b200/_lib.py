@@ -24,6 +24,7 @@ SIGNATURES = {
     "gg_eigh_workspace_bytes": (_sz, [_i, _i]),
     "gg_eigh": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _sz, _i, _i, _d, _i, _d, ctypes.POINTER(_i), _vp, _vp]),
     "gg_sytrd_profile": (_i, [_vp, _vp, _i, _i, _vp, _sz, _i, _vp]),
+    "gg_sytrd_write_depth": (_i, []),
     "gg_recon": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gg_sgl_nparts": (_i, [_i, _i]),
     "gg_prox_sgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _i, _vp, _vp, _vp]),

@@ -33,6 +33,7 @@ int gg_launch_ext_dual(double*, double*, const double*, const double*, const dou
                        const double*, const double*, const int*, int, int, double*, cudaStream_t);
 int gg_launch_prox_band(const double*, double*, const double*, double, double, int, int, int, int, int, cudaStream_t);
 size_t gg_tridiag_ws_bytes(int, int);
+int gg_tr_lazy_depth();
 int gg_gershgorin_min_impl(const double*, int, int, void*, size_t, double*, cudaStream_t);
 
 extern "C" {
@@ -43,6 +44,8 @@ int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_byt
     if (ws_bytes < gg_tridiag_ws_bytes(M, p)) return -3;
     return gg_eigh_tridiag_impl(A, D, M, p, nullptr, 1, ws, ws_bytes, (cudaStream_t)stream, which == 0 ? 3 : which);
 }
+
+int gg_sytrd_write_depth(void) { return gg_tr_lazy_depth(); }
 
 int gg_version(void) { return 100; }
 

@@ -5,9 +5,11 @@
 // for p > GG_SMALL_MAX.  Same three stages as dsyevd (dsytrd, dstedc, dormtr), laid out for the GPU:
 //
 //   1. sytrd   A = Q_H T Q_H^T.  Per column j two launches over the whole batch:
-//              tr_col_kernel (one CTA per matrix: finish w_{j-1}, form the Householder vector v_j from
-//              the already updated row j) and tr_symv_kernel (streams the trailing matrix once: applies
-//              the pending rank-2 update of step j-1 and accumulates y_j = A v_j in the same pass).
+//              tr_col_kernel (one CTA per matrix: finish w_{j-1}, apply the pending rank-2 updates to row j
+//              and form the Householder vector v_j) and tr_symv_kernel (streams the upper triangle of the
+//              trailing matrix once: applies the pending rank-2 updates in registers, accumulates the full
+//              y_j = A v_j from that half pass and stores the block only every q-th pass, see TR_QMAX).
+//              The last TR_TAIL columns run in shared memory in one launch (tr_tail_kernel).
 //   2. stedc   Cuppen divide & conquer with Gu/Eisenstat's stable eigenvector formula: rank-one tearing
 //              at every split, leaves (<=32) by the shared-memory Jacobi kernel, then level-synchronous
 //              merges: deflation (dc_prepare), secular equation (dc_secular, one warp per root),
@@ -36,97 +38,159 @@ struct TrWs {
     double* d;       // (M,n)
     double* e;       // (M,n)
     double* vbuf;    // (M,2,n)
-    double* w;       // (M,n)
+    double* w;       // (M,TR_QMAX,n) ring of the w vectors of the pending (not yet written back) rank-2 updates
     double* y;       // (M,n)
 };
 
-// One CTA per matrix.  j in [0, n-1].
-__global__ void __launch_bounds__(1024)
-tr_col_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip)
+// Lazy write-back of the rank-2 updates: the trailing block in memory may lag behind by up to TR_QMAX Householder
+// steps.  Pass j re-applies the pending pairs (v_k, w_k), k in [kb, j-1], to each tile in registers (the same
+// sequence of roundings as writing every pass), and only every q-th pass stores the tiles.  A read-only pass moves
+// 8 B per element instead of 16.
+#define TR_QMAX 4
+
+__device__ __forceinline__ double tr_warp_allsum(double v)
 {
-    __shared__ double red[64];
-    __shared__ double s_bc[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result in every thread (fixed order => deterministic); one barrier; scratch >= 32 doubles
+__device__ __forceinline__ double tr_block_allsum(double v, double* scratch)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = tr_warp_allsum(v);
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    return tr_warp_allsum(lane < nw ? scratch[lane] : 0.0);
+}
+
+// One CTA per matrix, step j in [0, n-1];  kb = first pending pair (pairs kb..j-1 are not yet applied to A in memory).
+// Finishes w_{j-1} from the accumulated y, applies the pending updates to row j and forms the Householder vector
+// v_j.  The step sits on the critical path of the launch chain, so every independent global load (row j, y,
+// v_{j-1}) is issued up front into registers: the dependent chain is one memory round trip, two block reductions
+// (one barrier each) and the stores.   Element i = j + tid + e*blockDim.x, e < EPT.
+template <int EPT, int THR>
+__global__ void __launch_bounds__(THR)
+tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const int* __restrict__ skip)
+{
+    __shared__ double red1[32], red2[32];
+    __shared__ double s_a1;
     const int m = blockIdx.x;
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
     if (skip && skip[m]) return;
     const int tid = threadIdx.x, nt = blockDim.x;
-    double* Am = A + (size_t)m * n * n;
-    double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;    // v^{(j-1)}
-    double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n;           // v^{(j)}
-    double* w = ws.w + (size_t)m * n;
-    const double* y = ws.y + (size_t)m * n;
+    const double* rowj = A + (size_t)m * n * n + (size_t)j * n;
+    const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;    // v^{(j-1)}
+    double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n;                 // v^{(j)}
+    double* wring = ws.w + (size_t)m * TR_QMAX * n;
+    const double* Vhm = ws.Vh + (size_t)m * n * n;
+    double* y = ws.y + (size_t)m * n;
     double* tau = ws.tau + (size_t)m * n;
+    const int cnt = j - kb;
 
-    double wj = 0.0;
-    if (j >= 1) {
-        // finish w^{(j-1)} = p + alpha v, p = tau*y, alpha = -tau/2 * (p.v), on indices j..n-1
-        const double tp = tau[j - 1];
-        double part[1] = {0.0};
-        for (int i = j + tid; i < n; i += nt) part[0] += (tp * y[i]) * vprev[i];
-        gg_block_sum<1>(part, red);
-        if (tid == 0) s_bc[0] = -0.5 * tp * part[0];
-        __syncthreads();
-        const double alpha = s_bc[0];
-        for (int i = j + tid; i < n; i += nt) w[i] = tp * y[i] + alpha * vprev[i];
-        __syncthreads();
-        wj = w[j];                                   // v^{(j-1)}[j] = 1
+    double a[EPT], yv[EPT], vp[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = j + tid + e * nt;
+        const bool ok = i < n;
+        a[e] = ok ? rowj[i] : 0.0;
+        yv[e] = (ok && j >= 1) ? y[i] : 0.0;
+        vp[e] = (ok && j >= 1) ? vprev[i] : 0.0;
     }
-    // y is accumulated with atomics by the next tr_symv_kernel: clear it now that it has been consumed
+    double tp = 0.0, yj = 0.0;
+    if (j >= 1) { tp = tau[j - 1]; yj = y[j]; }
+    // older pending pairs kb..j-2 (independent of w_{j-1}): a_i -= v_k[i] w_k[j] + w_k[i] v_k[j]
+    // (fully unrolled with predicates so that all of these loads are in flight together with the ones above)
     {
-        double* yz = ws.y + (size_t)m * n;
-        for (int i = tid; i < n; i += nt) yz[i] = 0.0;
-    }
-    // row j (== column j) of the trailing block, with the pending update of step j-1 applied
-    // a_i = A[j][i] - v_i w_j - w_i v_j ,  i in j..n-1
-    double* rowj = Am + (size_t)j * n;
-    double part[1] = {0.0};
-    for (int i = j + tid; i < n; i += nt) {
-        double a = rowj[i];
-        if (j >= 1) a = a - vprev[i] * wj - w[i];    // v_j = 1
-        rowj[i] = a;
-        if (i >= j + 2) part[0] += a * a;
-    }
-    gg_block_sum<1>(part, red);
-    __syncthreads();
-    if (tid == 0) {
-        ws.d[(size_t)m * n + j] = rowj[j];
-        if (j < n - 1) {
-            const double alpha = rowj[j + 1];
-            const double xn2 = part[0];
-            double t = 0.0, beta = alpha, scale = 0.0;
-            if (xn2 > 0.0) {
-                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-                t = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+        double wkj[TR_QMAX - 1], vkj[TR_QMAX - 1], wki[TR_QMAX - 1][EPT], vki[TR_QMAX - 1][EPT];
+#pragma unroll
+        for (int q = 0; q < TR_QMAX - 1; ++q) {
+            const bool on = q < cnt - 1;
+            const int k = on ? kb + q : 0;
+            const double* wk = wring + (size_t)(k % TR_QMAX) * n;
+            const double* vk = Vhm + (size_t)k * n;
+            wkj[q] = on ? wk[j] : 0.0;
+            vkj[q] = on ? vk[j] : 0.0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = j + tid + e * nt;
+                wki[q][e] = (on && i < n) ? wk[i] : 0.0;
+                vki[q][e] = (on && i < n) ? vk[i] : 0.0;
             }
-            tau[j] = t;
-            ws.e[(size_t)m * n + j] = beta;
-            s_bc[1] = scale;
+        }
+#pragma unroll
+        for (int q = 0; q < TR_QMAX - 1; ++q)
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (q < cnt - 1) a[e] = a[e] - vki[q][e] * wkj[q] - wki[q][e] * vkj[q];
+    }
+    if (j >= 1) {
+        // w^{(j-1)} = p + alpha v, p = tau*y, alpha = -tau/2 * (p.v), on indices j..n-1;  v^{(j-1)}[j] = 1
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) part += (tp * yv[e]) * vp[e];
+        const double alpha = -0.5 * tp * tr_block_allsum(part, red1);      // (barrier: every read of y is done)
+        const double wj = tp * yj + alpha;
+        double* w = wring + (size_t)((j - 1) % TR_QMAX) * n;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = j + tid + e * nt;
+            if (i < n) {
+                const double wi = tp * yv[e] + alpha * vp[e];
+                w[i] = wi;
+                a[e] = a[e] - vp[e] * wj - wi;
+            }
         }
     }
-    __syncthreads();
+    double part2 = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = j + tid + e * nt;
+        if (i < n) y[i] = 0.0;        // consumed: clear for the atomics of the next tr_symv_kernel (indices > j)
+        if (i < n && i >= j + 2) part2 += a[e] * a[e];
+        if (i == j + 1 && i < n) s_a1 = a[e];
+        if (i == j) ws.d[(size_t)m * n + j] = a[e];
+    }
+    const double xn2 = tr_block_allsum(part2, red2);
     if (j < n - 1) {
-        const double scale = s_bc[1];
+        const double alpha = s_a1;
+        double t = 0.0, beta = alpha, scale = 0.0;
+        if (xn2 > 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+            t = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        if (tid == 0) {
+            tau[j] = t;
+            ws.e[(size_t)m * n + j] = beta;
+        }
         double* vh = ws.Vh + (size_t)m * n * n + (size_t)j * n;
-        for (int i = j + 1 + tid; i < n; i += nt) {
-            const double v = (i == j + 1) ? 1.0 : rowj[i] * scale;
-            vcur[i] = v;
-            vh[i] = v;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = j + tid + e * nt;
+            if (i < n && i >= j + 1) {
+                const double v = (i == j + 1) ? 1.0 : a[e] * scale;
+                vcur[i] = v;
+                vh[i] = v;
+            }
         }
     }
 }
 
-// Streams the UPPER triangle of the trailing block, one CTA per 64x64 tile (I <= J): applies the pending
-// rank-2 update of step j-1 (a_rc -= vp_r w_c + w_r vp_c), writes the tile back, and accumulates the full
-// symmetric y = A v from that single pass: y_I += T v_J (row sums) and, mirrored, y_J += T^T v_I (column sums;
-// strictly upper part on diagonal tiles).  Half the traffic of a full-matrix pass; 128 FP64 atomics per tile.
+// Streams the UPPER triangle of the trailing block, one CTA per 64x64 tile (I <= J): applies the pending rank-2
+// updates kb..j-1 (a_rc -= v_k[r] w_k[c] + w_k[r] v_k[c]) in registers, stores the tile only on a write pass, and
+// accumulates the full symmetric y = A v from that single pass: y_I += T v_J (row sums) and, mirrored,
+// y_J += T^T v_I (column sums; strictly upper part on diagonal tiles).  Each thread owns a 4 x 4 register block
+// (rows 4*ty+i, columns tx+16*jj: a half warp reads 128 contiguous bytes of a row); the tile loads are issued before
+// anything else, the row sums are reduced with shuffles over the 16 lanes of a half warp and the column sums over
+// the 16 row groups through a small shared array.  128 FP64 atomics per tile.
 #define SV_T 64
-__global__ void __launch_bounds__(256)
-tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restrict__ skip, int nt)
+__global__ void __launch_bounds__(256, 3)
+tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt)
 {
-    __shared__ double tile[SV_T][SV_T + 1];
-    __shared__ double s_vpI[SV_T], s_wI[SV_T], s_vI[SV_T], s_vpJ[SV_T], s_wJ[SV_T], s_vJ[SV_T];
+    __shared__ double s_vp[TR_QMAX][2][SV_T], s_w[TR_QMAX][2][SV_T], s_vI[SV_T], s_vJ[SV_T], s_col[8][SV_T], s_row[SV_T];
     // Boustrophedon sweep: consecutive launches walk the (matrix, tile) space in opposite directions, so a launch
     // starts with the tiles the previous one touched last -- they are still in L2 (an identical sweep order is the
     // worst case for an LRU-like cache when the ~80 MB working set exceeds the usable capacity).
@@ -141,73 +205,106 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, TrWs ws, const int* __restr
     asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
     if (skip && skip[m]) return;
     const int r0 = I * SV_T, c0 = J * SV_T;
-    const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n + base;
-    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
-    const double* w = ws.w + (size_t)m * n + base;
-    const bool pend = (j >= 1);
-    const int tid = threadIdx.x;
-    if (tid < SV_T) {
-        const int r = r0 + tid;
-        const bool ok = r < t;
-        s_vpI[tid] = (ok && pend) ? vprev[r] : 0.0;
-        s_wI[tid] = (ok && pend) ? w[r] : 0.0;
-        s_vI[tid] = ok ? vcur[r] : 0.0;
-    } else if (tid < 2 * SV_T) {
-        const int c = c0 + tid - SV_T;
-        const bool ok = c < t;
-        s_vpJ[tid - SV_T] = (ok && pend) ? vprev[c] : 0.0;
-        s_wJ[tid - SV_T] = (ok && pend) ? w[c] : 0.0;
-        s_vJ[tid - SV_T] = ok ? vcur[c] : 0.0;
-    }
-    __syncthreads();
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int rb = r0 + 4 * ty, cb = c0 + tx;
     double* Am = A + (size_t)m * n * n + (size_t)base * n + base;
-    const int cl = tid & 63, rq = tid >> 6;          // column in tile, row quarter
-    const int c = c0 + cl;
-    double a[16];
+    double a[4][4];
+    unsigned okm = 0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int r = r0 + rq + 4 * q;
-        a[q] = (r < t && c < t && c >= r) ? Am[(size_t)r * n + c] : 0.0;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int r = rb + i, c = cb + 16 * jj;
+            const bool ok = (r < t && c < t && c >= r);
+            okm |= ok ? (1u << (4 * i + jj)) : 0u;
+            a[i][jj] = ok ? Am[(size_t)r * n + c] : 0.0;
+        }
+    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
+    const double* wring = ws.w + (size_t)m * TR_QMAX * n + base;
+    const double* Vhm = ws.Vh + (size_t)m * n * n + base;
+    const int cnt = j - kb;
+    for (int e = tid; e < cnt * 2 * SV_T; e += 256) {
+        const int q = e >> 7, h = (e >> 6) & 1, l = e & 63, k = kb + q;
+        const int pos = (h ? c0 : r0) + l;
+        const bool ok = pos < t;
+        s_vp[q][h][l] = ok ? Vhm[(size_t)k * n + pos] : 0.0;
+        s_w[q][h][l] = ok ? wring[(size_t)(k % TR_QMAX) * n + pos] : 0.0;
     }
-    if (pend) {
-        const double wc = s_wJ[cl], vpc = s_vpJ[cl];
+    if (tid < SV_T) s_vI[tid] = (r0 + tid < t) ? vcur[r0 + tid] : 0.0;
+    else if (tid < 2 * SV_T) s_vJ[tid - SV_T] = (c0 + tid - SV_T < t) ? vcur[c0 + tid - SV_T] : 0.0;
+    __syncthreads();
+    // pending updates, oldest first.  Out-of-range rows / columns carry zeros in the staged vectors, so only the
+    // lower part of a diagonal tile has to be masked (it must stay zero for the sums below).
+    for (int k = 0; k < cnt; ++k) {
+        double wc[4], vc[4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int rl = rq + 4 * q, r = r0 + rl;
-            if (r < t && c < t && c >= r) {
-                a[q] = a[q] - s_vpI[rl] * wc - s_wI[rl] * vpc;
-                Am[(size_t)r * n + c] = a[q];
-            }
+        for (int jj = 0; jj < 4; ++jj) { wc[jj] = s_w[k][1][tx + 16 * jj]; vc[jj] = s_vp[k][1][tx + 16 * jj]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double vr = s_vp[k][0][4 * ty + i], wr = s_w[k][0][4 * ty + i];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) a[i][jj] = a[i][jj] - vr * wc[jj] - wr * vc[jj];
         }
     }
+    if (I == J && cnt > 0) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) tile[rq + 4 * q][cl] = a[q];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (!(okm & (1u << (4 * i + jj)))) a[i][jj] = 0.0;
+    }
+    if (write) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (okm & (1u << (4 * i + jj))) Am[(size_t)(rb + i) * n + cb + 16 * jj] = a[i][jj];
+    }
+    double vJ[4], vI[4], row[4], col[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { vJ[q] = s_vJ[tx + 16 * q]; vI[q] = s_vI[4 * ty + q]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) s = fma(a[i][jj], vJ[jj], s);
+        row[i] = s;                                      // includes the diagonal
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool dg = (I == J) && (rb + i == cb + 16 * jj);   // mirrored part: strictly upper only
+            s = fma(dg ? 0.0 : a[i][jj], vI[i], s);
+        }
+        col[jj] = s;
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row[i] += __shfl_xor_sync(0xffffffffu, row[i], o);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) col[jj] += __shfl_xor_sync(0xffffffffu, col[jj], 16);
+    // stage both partial results so that the 128 atomics of the tile are four fully coalesced warp instructions
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_row[4 * ty + i] = row[i];
+    }
+    if ((tid & 16) == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) s_col[tid >> 5][tx + 16 * jj] = col[jj];
+    }
     __syncthreads();
     double* y = ws.y + (size_t)m * n + base;
-    // four independent accumulators per sum: the 64-term FMA chains are latency bound in the small-t regime
-    if (tid < SV_T) {                                  // row sums -> y_I (includes the diagonal)
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-        for (int cc = 0; cc < SV_T; cc += 4) {
-            s0 = fma(tile[tid][cc], s_vJ[cc], s0);
-            s1 = fma(tile[tid][cc + 1], s_vJ[cc + 1], s1);
-            s2 = fma(tile[tid][cc + 2], s_vJ[cc + 2], s2);
-            s3 = fma(tile[tid][cc + 3], s_vJ[cc + 3], s3);
-        }
-        if (r0 + tid < t) atomicAdd(y + r0 + tid, (s0 + s1) + (s2 + s3));
-    } else if (tid < 2 * SV_T) {                       // column sums -> y_J (strictly upper part only)
+    if (tid < SV_T) {
+        if (r0 + tid < t) atomicAdd(y + r0 + tid, s_row[tid]);
+    } else if (tid < 2 * SV_T) {
         const int cc = tid - SV_T;
-        const int rend = (I == J) ? cc : SV_T;         // diagonal tile: rows above the diagonal only
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int rr = 0;
-        for (; rr + 4 <= rend; rr += 4) {
-            s0 = fma(tile[rr][cc], s_vI[rr], s0);
-            s1 = fma(tile[rr + 1][cc], s_vI[rr + 1], s1);
-            s2 = fma(tile[rr + 2][cc], s_vI[rr + 2], s2);
-            s3 = fma(tile[rr + 3][cc], s_vI[rr + 3], s3);
-        }
-        for (; rr < rend; ++rr) s0 = fma(tile[rr][cc], s_vI[rr], s0);
-        if (c0 + cc < t) atomicAdd(y + c0 + cc, (s0 + s1) + (s2 + s3));
+        double s = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += s_col[w8][cc];
+        if (c0 + cc < t) atomicAdd(y + c0 + cc, s);
     }
 }
 
@@ -989,6 +1086,19 @@ static int dc_levels(int n)
     return L;
 }
 
+// write-back depth of the tridiagonalisation (see TR_QMAX): env GG_TR_LAZY in [1, TR_QMAX], default 3
+int gg_tr_lazy_depth()
+{
+    static int q = -1;
+    if (q < 0) {
+        const char* ev = getenv("GG_TR_LAZY");
+        q = ev ? atoi(ev) : 3;
+        if (q < 1) q = 1;
+        if (q > TR_QMAX) q = TR_QMAX;
+    }
+    return q;
+}
+
 size_t gg_tridiag_ws_bytes(int M, int n)
 {
     const size_t nn = (size_t)n * n, Mn = (size_t)M * n;
@@ -997,7 +1107,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     size_t b = 0;
     b += 3 * al(sizeof(double) * M * nn);                 // Vh, Q0, U
     b += 12 * al(sizeof(double) * Mn);                    // tau d e vbuf(2) w y lam0 lam1 z dl wnd zhat (13) -> see below
-    b += 2 * al(sizeof(double) * Mn);
+    b += (2 + TR_QMAX) * al(sizeof(double) * Mn);
     b += 3 * al(sizeof(int) * Mn) + 2 * al(sizeof(double) * Mn);   // ndrow, rotp, rotn, rotc, rots
     b += al(sizeof(int) * (size_t)M * (1 << L));          // nodek
     b += al(sizeof(double) * (size_t)M * (1 << L));       // noderho
@@ -1026,7 +1136,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     tw.d = (double*)take(sizeof(double) * Mn);
     tw.e = (double*)take(sizeof(double) * Mn);
     tw.vbuf = (double*)take(sizeof(double) * 2 * Mn);
-    tw.w = (double*)take(sizeof(double) * Mn);
+    tw.w = (double*)take(sizeof(double) * TR_QMAX * Mn);
     tw.y = (double*)take(sizeof(double) * Mn);
     dw.lam[0] = (double*)take(sizeof(double) * Mn);
     dw.lam[1] = (double*)take(sizeof(double) * Mn);
@@ -1068,19 +1178,31 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         cfg.attrs = pdl;
         cfg.numAttrs = 1;
         const int js = (which == 1 || which == 2) ? n : (n > TR_TAIL ? n - TR_TAIL : 0);   // tail takes over at column js
+        const int lazy_q = gg_tr_lazy_depth();
+        int kb = 0;                                   // pairs kb..j-1 are pending at step j
         for (int j = 0; j < js; ++j) {
             if (which != 2) {
-                cfg.gridDim = dim3(M); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0;
-                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_col_kernel, A, n, j, tw, (const int*)skip);
+                const int len = n - j;
+                const int thr = len <= 2048 ? 256 : 1024;
+                cfg.gridDim = dim3(M); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = 0;
+                cudaError_t e;
+                if (len <= 512) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<2, 256>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else if (len <= 1024) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<4, 256>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else if (len <= 2048) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 256>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else if (len <= 8192) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 1024>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else return -5;
                 if (e != cudaSuccess) return (int)e;
             }
+            // write pass: the pending list is full, or the tail kernel takes over next (it expects only pair js-1)
+            const int write = (j - kb >= lazy_q || (j == js - 1 && j > kb)) ? 1 : 0;
             if (j < n - 1 && which != 1) {
                 const int t = n - j - 1;
                 const int nt = (t + SV_T - 1) / SV_T;
                 cfg.gridDim = dim3(nt * (nt + 1) / 2, M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
-                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, tw, (const int*)skip, nt);
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, kb, write, tw, (const int*)skip, nt);
                 if (e != cudaSuccess) return (int)e;
             }
+            if (write) kb = j;
         }
         if (js < n) {
             const int ts = n - js;

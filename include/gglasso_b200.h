@@ -58,8 +58,13 @@ int gg_eigh(double* A, double* D, int M, int p, const double* ctrl, int mpp, voi
 
 /* Stage 1 of the large-p eigensolver only (Householder tridiagonalisation of the batch), for profiling:
  * which = 0 full sytrd, 1 only the per-column kernels, 2 only the trailing-matrix (symv + rank-2 update)
- * kernels.  Results of which != 0 are meaningless; A is destroyed.  p must exceed 160. */
+ * kernels.  Results of which != 0 are meaningless; A is destroyed.  p must exceed 32. */
 int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_bytes, int which, void* stream);
+
+/* Write-back depth q of the trailing-matrix kernel: pass j stores the updated trailing block only when q rank-2
+ * updates are pending (every q-th pass moves 16 B per element, the others 8 B).  Needed to state the algorithmic
+ * bytes of a launch; 1 <= q <= 4 (environment GG_TR_LAZY, default 3). */
+int gg_sytrd_write_depth(void);
 
 /* Out = V diag(f(D)) V^T with V^T = Vt from gg_eigh (FP64 tensor cores, exactly symmetric result).
  * mode 0: f = phi+(d, beta) = (sqrt(d^2+4 beta)+d)/2   src/gglasso/solver/ggl_helper.py:272-303

@@ -626,3 +626,20 @@ def test_ext_admm_consistent_with_conforming_solver(golden):
     (sm, _), _ = _quiet(ADMM_MGL, S, 0.05, 0.02, "GGL", np.repeat(np.eye(p)[None], K, 0), tol=1e-9, rtol=1e-9)
     for k in range(K):
         assert np.abs(se["Theta"][k] - sm["Theta"][k]).max() < 1e-4
+
+
+@pytest.mark.parametrize("p", [6990, 7100])
+def test_eigh_size_limits(p):
+    """p = 6990: largest size on the tridiagonal divide & conquer path; p = 7100: the documented fallback to the
+    block-Jacobi path above 7000. Checked on the device (no host LAPACK at this size)."""
+    from gglasso_b200._engine import Eigh
+    g = torch.Generator(device="cuda").manual_seed(p)
+    A = torch.randn(p, p, dtype=torch.float64, device="cuda", generator=g)
+    A = ((A + A.T) / (2 * p ** 0.5)).contiguous()[None]
+    W = A.clone()
+    e = Eigh(1, p, torch.device("cuda"))
+    D = e.eigh(W, stream=torch.cuda.current_stream().cuda_stream)      # W -> Vt (rows = eigenvectors)
+    V = W[0]
+    resid = (V @ A[0] - D[0][:, None] * V).abs().max().item()
+    orth = (V @ V.T - torch.eye(p, dtype=torch.float64, device="cuda")).abs().max().item()
+    assert resid < 1e-11 and orth < 1e-11, (resid, orth)
