@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgglasso_b200.so")
+# GGLASSO_B200_LIB: alternative build of the same library (instrumented diagnostics builds, scripts/gpu_tr_timing.sh)
+LIB_PATH = os.environ.get("GGLASSO_B200_LIB") or os.path.join(_HERE, "libgglasso_b200.so")
 
 CTRL_STRIDE = 16
 HIST_STRIDE = 5

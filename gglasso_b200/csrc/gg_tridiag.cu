@@ -40,7 +40,22 @@ struct TrWs {
     double* vbuf;    // (M,2,n)
     double* w;       // (M,TR_QMAX,n) ring of the w vectors of the pending (not yet written back) rank-2 updates
     double* y;       // (M,n)
+#ifdef TR_TIMING
+    long long* dbg;  // (n,2,8) time stamps of one CTA per launch (instrumented build only)
+#endif
 };
+
+#ifdef TR_TIMING
+__device__ __forceinline__ long long tr_now()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TR_STAMP(kind, slot) do { if (tr_stamp_on) ws.dbg[((size_t)j * 2 + (kind)) * 8 + (slot)] = tr_now(); } while (0)
+#else
+#define TR_STAMP(kind, slot) do { } while (0)
+#endif
 
 // Lazy write-back of the rank-2 updates: the trailing block in memory may lag behind by up to TR_QMAX Householder
 // steps.  Pass j re-applies the pending pairs (v_k, w_k), k in [kb, j-1], to each tile in registers (the same
@@ -77,9 +92,14 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
     __shared__ double red1[32], red2[32];
     __shared__ double s_a1;
     const int m = blockIdx.x;
+#ifdef TR_TIMING
+    const bool tr_stamp_on = (blockIdx.x == 0 && threadIdx.x == 0);
+#endif
+    TR_STAMP(0, 0);
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
-    if (skip && skip[m]) return;
+    TR_STAMP(0, 1);
+    const int sk = skip ? skip[m] : 0;        // consumed below, after the other loads have been issued
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* rowj = A + (size_t)m * n * n + (size_t)j * n;
     const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;    // v^{(j-1)}
@@ -120,6 +140,8 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
                 vki[q][e] = (on && i < n) ? vk[i] : 0.0;
             }
         }
+        if (sk) return;                       // (block-uniform; no barrier has been passed yet)
+        TR_STAMP(0, 2);
 #pragma unroll
         for (int q = 0; q < TR_QMAX - 1; ++q)
 #pragma unroll
@@ -132,6 +154,7 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
 #pragma unroll
         for (int e = 0; e < EPT; ++e) part += (tp * yv[e]) * vp[e];
         const double alpha = -0.5 * tp * tr_block_allsum(part, red1);      // (barrier: every read of y is done)
+        TR_STAMP(0, 3);
         const double wj = tp * yj + alpha;
         double* w = wring + (size_t)((j - 1) % TR_QMAX) * n;
 #pragma unroll
@@ -154,6 +177,7 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
         if (i == j) ws.d[(size_t)m * n + j] = a[e];
     }
     const double xn2 = tr_block_allsum(part2, red2);
+    TR_STAMP(0, 4);
     if (j < n - 1) {
         const double alpha = s_a1;
         double t = 0.0, beta = alpha, scale = 0.0;
@@ -177,6 +201,7 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
             }
         }
     }
+    TR_STAMP(0, 5);
 }
 
 // Streams the UPPER triangle of the trailing block, one CTA per 64x64 tile (I <= J): applies the pending rank-2
@@ -201,9 +226,16 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
     int idx = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, I = 0;
     while (idx >= nt - I) { idx -= nt - I; ++I; }
     const int J = I + idx;
+#ifdef TR_TIMING
+    const bool tr_stamp_on = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+#endif
+    TR_STAMP(1, 0);
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
-    if (skip && skip[m]) return;
+    TR_STAMP(1, 1);
+    // Every global load of the CTA is issued here, back to back, before anything is consumed: the skip flag, the
+    // 4 x 4 register block of the tile and the slices of the pending / current vectors (one round trip in total).
+    const int sk = skip ? skip[m] : 0;
     const int r0 = I * SV_T, c0 = J * SV_T;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int rb = r0 + 4 * ty, cb = c0 + tx;
@@ -223,16 +255,32 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
     const double* wring = ws.w + (size_t)m * TR_QMAX * n + base;
     const double* Vhm = ws.Vh + (size_t)m * n * n + base;
     const int cnt = j - kb;
-    for (int e = tid; e < cnt * 2 * SV_T; e += 256) {
+    double pv[2], pw[2], cv = 0.0;            // staged element e = tid + 256 u: pair q = e/128, half h, lane l
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int e = tid + 256 * u;
         const int q = e >> 7, h = (e >> 6) & 1, l = e & 63, k = kb + q;
         const int pos = (h ? c0 : r0) + l;
-        const bool ok = pos < t;
-        s_vp[q][h][l] = ok ? Vhm[(size_t)k * n + pos] : 0.0;
-        s_w[q][h][l] = ok ? wring[(size_t)(k % TR_QMAX) * n + pos] : 0.0;
+        const bool ok = (q < cnt) && (pos < t);
+        pv[u] = ok ? Vhm[(size_t)k * n + pos] : 0.0;
+        pw[u] = ok ? wring[(size_t)(k % TR_QMAX) * n + pos] : 0.0;
     }
-    if (tid < SV_T) s_vI[tid] = (r0 + tid < t) ? vcur[r0 + tid] : 0.0;
-    else if (tid < 2 * SV_T) s_vJ[tid - SV_T] = (c0 + tid - SV_T < t) ? vcur[c0 + tid - SV_T] : 0.0;
+    if (tid < 2 * SV_T) {
+        const int pos = (tid < SV_T) ? r0 + tid : c0 + tid - SV_T;
+        cv = (pos < t) ? vcur[pos] : 0.0;
+    }
+    if (sk) return;                           // (block-uniform; no barrier has been passed yet)
+    TR_STAMP(1, 2);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int e = tid + 256 * u;
+        (&s_vp[0][0][0])[e] = pv[u];
+        (&s_w[0][0][0])[e] = pw[u];
+    }
+    if (tid < SV_T) s_vI[tid] = cv;
+    else if (tid < 2 * SV_T) s_vJ[tid - SV_T] = cv;
     __syncthreads();
+    TR_STAMP(1, 3);
     // pending updates, oldest first.  Out-of-range rows / columns carry zeros in the staged vectors, so only the
     // lower part of a diagonal tile has to be masked (it must stay zero for the sums below).
     for (int k = 0; k < cnt; ++k) {
@@ -260,6 +308,10 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
             for (int jj = 0; jj < 4; ++jj)
                 if (okm & (1u << (4 * i + jj))) Am[(size_t)(rb + i) * n + cb + 16 * jj] = a[i][jj];
     }
+#ifdef TR_TIMING
+    if (a[0][0] == 1.2345e300) return;       // (forces the tile loads to have landed before the stamp)
+#endif
+    TR_STAMP(1, 4);
     double vJ[4], vI[4], row[4], col[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { vJ[q] = s_vJ[tx + 16 * q]; vI[q] = s_vI[4 * ty + q]; }
@@ -296,6 +348,7 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
         for (int jj = 0; jj < 4; ++jj) s_col[tid >> 5][tx + 16 * jj] = col[jj];
     }
     __syncthreads();
+    TR_STAMP(1, 5);
     double* y = ws.y + (size_t)m * n + base;
     if (tid < SV_T) {
         if (r0 + tid < t) atomicAdd(y + r0 + tid, s_row[tid]);
@@ -306,6 +359,7 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
         for (int w8 = 0; w8 < 8; ++w8) s += s_col[w8][cc];
         if (c0 + cc < t) atomicAdd(y + c0 + cc, s);
     }
+    TR_STAMP(1, 6);
 }
 
 // Tail of the tridiagonalisation: once the trailing block has at most TR_TAIL rows it fits in shared memory, and
@@ -1158,6 +1212,9 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     static int stop_after = -1;
     if (stop_after < 0) { const char* ev = getenv("GG_TR_STOP"); stop_after = ev ? atoi(ev) : 0; }
 
+#ifdef TR_TIMING
+    tw.dbg = (long long*)dw.U;            // U is not used before stage 2; read back by the timing script
+#endif
     tr_skip_kernel<<<(M + 127) / 128, 128, 0, s>>>(ctrl, mpp, M, skip);
     GG_CHECK_LAUNCH();
     dim3 gz(64, M);
