@@ -803,38 +803,50 @@ dc_secular_kernel(int n, int level, double* __restrict__ lam_out, DcWs ws, const
 }
 
 // Loewner formula: zhat_i = sign(w_i) sqrt(-Delta_ii prod_{j!=i} Delta_ji/(dl_i - dl_j))
-__global__ void __launch_bounds__(256)
+// Block = 64 columns i x ZH_G row groups: group g multiplies up the factors of rows j = g (mod ZH_G) chunks, the
+// partial products are combined through shared memory (the product over 1000 factors is a serial chain per
+// thread; more threads per column is the only way to shorten it).
+#define ZH_C 64
+#define ZH_G 8
+__global__ void __launch_bounds__(ZH_C * ZH_G)
 dc_zhat_kernel(int n, int level, DcWs ws, const int* __restrict__ skip)
 {
+    __shared__ double s_part[ZH_G][ZH_C];
     const int m = blockIdx.z;
     if (skip && skip[m]) return;
     const int node = blockIdx.y;
     const int k = ws.nodek[(size_t)m * ws.nodes_max + node];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= k) return;
+    if ((int)blockIdx.x * ZH_C >= k) return;
+    const int ix = threadIdx.x & (ZH_C - 1), g = threadIdx.x / ZH_C;
+    const int i = blockIdx.x * ZH_C + ix;
     const int lo = dc_bnd(n, level, node);
     const double* dl = ws.dl + (size_t)m * n + lo;
     const double* Dm = ws.U + (size_t)m * n * n + (size_t)lo * n + lo;
-    const double di = dl[i];
-    // four independent partial products: the FP64 divisions are latency bound, not throughput bound
-    // numerators and denominators are multiplied up in chunks of 8 terms (each factor lies in [1e-16, 4] after the
-    // normalisation of T, so a chunk cannot over/underflow) and divided once per chunk: 8x fewer FP64 divisions
-    double prod = Dm[(size_t)i * n + i];
-    int j = 0;
-    for (; j + 8 <= k; j += 8) {
-        double num = 1.0, den = 1.0;
+    double prod = 1.0;
+    if (i < k) {
+        const double di = dl[i];
+        // numerators and denominators are multiplied up in chunks of 8 terms (each factor lies in [1e-16, 4] after
+        // the normalisation of T, so a chunk cannot over/underflow) and divided once per chunk
+        for (int j0 = 8 * g; j0 < k; j0 += 8 * ZH_G) {
+            double num = 1.0, den = 1.0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int jj = j + u;
-            const bool self = (jj == i);
-            num *= self ? 1.0 : Dm[(size_t)jj * n + i];
-            den *= self ? 1.0 : (di - dl[jj]);
+            for (int u = 0; u < 8; ++u) {
+                const int jj = j0 + u;
+                const bool use = (jj < k) && (jj != i);
+                num *= use ? Dm[(size_t)jj * n + i] : 1.0;
+                den *= use ? (di - dl[jj]) : 1.0;
+            }
+            prod *= num / den;
         }
-        prod *= num / den;
     }
-    for (; j < k; ++j)
-        if (j != i) prod *= Dm[(size_t)j * n + i] / (di - dl[j]);
-    ws.zhat[(size_t)m * n + lo + i] = copysign(sqrt(-prod), ws.wnd[(size_t)m * n + lo + i]);
+    s_part[g][ix] = prod;
+    __syncthreads();
+    if (g == 0 && i < k) {
+        double p = Dm[(size_t)i * n + i];
+#pragma unroll
+        for (int q = 0; q < ZH_G; ++q) p *= s_part[q][ix];
+        ws.zhat[(size_t)m * n + lo + i] = copysign(sqrt(-p), ws.wnd[(size_t)m * n + lo + i]);
+    }
 }
 
 // U[j][i] = zhat_i / Delta[j][i], rows normalised (row j = eigenvector j of D + rho z z^T)
@@ -1307,7 +1319,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         dc_prepare_kernel<<<dim3(nodes, M), 1024, psm, s>>>(tw.e, n, l, dw.lam[(l + 1) & 1], dw.lam[l & 1],
                                                             (double*)Qin, Qout, dw, skip);
         dc_secular_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, sizeof(double) * 2 * Nmax, s>>>(n, l, dw.lam[l & 1], dw, skip);
-        dc_zhat_kernel<<<dim3((Nmax + 255) / 256, nodes, M), 256, 0, s>>>(n, l, dw, skip);
+        dc_zhat_kernel<<<dim3((Nmax + ZH_C - 1) / ZH_C, nodes, M), ZH_C * ZH_G, 0, s>>>(n, l, dw, skip);
         dc_vectors_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, 0, s>>>(n, l, dw, skip);
         dc_gemm_kernel<<<dim3((Nmax + DG_T - 1) / DG_T, (Nmax + DG_T - 1) / DG_T, nodes * M), 256, 0, s>>>(n, l, Qin, Qout, dw, skip);
         GG_CHECK_LAUNCH();
