@@ -1117,6 +1117,221 @@ bt_apply_kernel(double* __restrict__ Q, const double* __restrict__ Vh, const dou
     }
 }
 
+// ---- blocked back-transformation for larger n ---------------------------------------------------------------
+// bt_apply_kernel walks 32-reflector panels; every panel re-reads the CTA's band of Vt twice and writes it once,
+// which makes the stage L2-bandwidth bound (measured 25% of the DMMA peak).  For n >= BB_MIN the reflectors are
+// grouped into blocks of BB_NB = 128 and each block is applied with two real GEMMs:
+//     Vt <- Vt H_{j0+127} ... H_{j0} = Vt - (Vt V^T) (X V),      V = rows j0..j0+127 of Vh (128 x n)
+// where X = T^T is the lower triangular matrix of the backward recurrence
+//     w_i = tau_i ( y_i - sum_{q>i} w_q G_qi ),  G = V V^T  =>  X[a][i] = -tau_i sum_{q=i+1..a} X[a][q] G[q][i],  X[a][a] = tau_a.
+// G, X and V' = X V do not depend on Vt and are formed for all blocks at once (three launches); the blocks are
+// then applied last to first with Y = Vt V^T (bb_y_kernel) and Vt -= Y V' (bb_upd_kernel).  All five products run
+// on the FP64 tensor cores through one 64x64-tile routine (cp.async double buffer, as dc_gemm_kernel).
+#define BB_NB 128
+#define BB_MIN 256
+#define BB_T 64
+#define BB_KC 16
+
+struct BbSmem {
+    double As[2][BB_T][BB_KC + 4];
+    double Bs[2][BB_T * (BB_KC + 4)];            // NT: [c][k] stride KC+4 ; NN: [k][c] stride BB_T+4 (fits: 16*68 <= 64*20)
+};
+
+// acc += A[r0.., 0..K) * op(B): NT: op(B)[k][c] = B[c*ldb + k];  NN: op(B)[k][c] = B[k*ldb + c].
+// Rows r >= Mr / columns c >= Nc / k >= K read as zero.  Fragment layout of gg_dmma (see gg_common.cuh).
+template <bool TRANSB>
+__device__ __forceinline__ void bb_gemm_tile(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                             int Mr, int Nc, int K, int r0, int c0, double (&acc)[2][4][2], BbSmem& sm)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int wr = wid >> 1, wc = wid & 1;          // 4 x 2 warps, 16 x 32 outputs each
+    const int nchunks = (K + BB_KC - 1) / BB_KC;
+    auto load_chunk = [&](int ch, int buf) {
+        const int k0 = ch * BB_KC;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = tid + 256 * q;
+            const int rr = idx / BB_KC, kk = idx % BB_KC;
+            double* dst = &sm.As[buf][rr][kk];
+            if (r0 + rr < Mr && k0 + kk < K) gg_cp_async8(dst, A + (size_t)(r0 + rr) * lda + k0 + kk);
+            else *dst = 0.0;
+        }
+        if (TRANSB) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + 256 * q;
+                const int cc = idx / BB_KC, kk = idx % BB_KC;
+                double* dst = &sm.Bs[buf][cc * (BB_KC + 4) + kk];
+                if (c0 + cc < Nc && k0 + kk < K) gg_cp_async8(dst, B + (size_t)(c0 + cc) * ldb + k0 + kk);
+                else *dst = 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + 256 * q;
+                const int kk = idx / BB_T, cc = idx % BB_T;
+                double* dst = &sm.Bs[buf][kk * (BB_T + 4) + cc];
+                if (c0 + cc < Nc && k0 + kk < K) gg_cp_async8(dst, B + (size_t)(k0 + kk) * ldb + c0 + cc);
+                else *dst = 0.0;
+            }
+        }
+        gg_cp_commit();
+    };
+    load_chunk(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) { load_chunk(ch + 1, (ch + 1) & 1); gg_cp_wait<1>(); }
+        else gg_cp_wait<0>();
+        __syncthreads();
+        const int buf = ch & 1;
+#pragma unroll
+        for (int k0 = 0; k0 < BB_KC; k0 += 4) {
+            double fa[2], fb[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) fa[a] = sm.As[buf][(wr * 2 + a) * 8 + fr][k0 + fc];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                fb[b] = TRANSB ? sm.Bs[buf][((wc * 4 + b) * 8 + fr) * (BB_KC + 4) + k0 + fc]
+                               : sm.Bs[buf][(k0 + fc) * (BB_T + 4) + (wc * 4 + b) * 8 + fr];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) gg_dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+        }
+        __syncthreads();
+    }
+}
+
+// C[r][c] = acc (SUB: C[r][c] -= acc) for the 64x64 tile at (r0, c0), bounds Mr x Nc
+template <bool SUB>
+__device__ __forceinline__ void bb_store_tile(double* __restrict__ C, int ldc, int Mr, int Nc, int r0, int c0,
+                                              const double (&acc)[2][4][2])
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int fr = lane >> 2, fc = lane & 3, wr = wid >> 1, wc = wid & 1;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int r = r0 + (wr * 2 + a) * 8 + fr;
+        if (r < Mr) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = c0 + (wc * 4 + b) * 8 + 2 * fc;
+                double* dst = C + (size_t)r * ldc + c;
+                if (c < Nc) dst[0] = SUB ? dst[0] - acc[a][b][0] : acc[a][b][0];
+                if (c + 1 < Nc) dst[1] = SUB ? dst[1] - acc[a][b][1] : acc[a][b][1];
+            }
+        }
+    }
+}
+
+#define BB_ZERO_ACC(acc)                                                          \
+    _Pragma("unroll") for (int a_ = 0; a_ < 2; ++a_)                                \
+        _Pragma("unroll") for (int b_ = 0; b_ < 4; ++b_) { acc[a_][b_][0] = 0.0; acc[a_][b_][1] = 0.0; }
+
+// G_P = V_P V_P^T for every block P of every matrix.  grid (2, 2, M*npb)
+__global__ void __launch_bounds__(256)
+bb_gram_kernel(const double* __restrict__ Vh, int n, int npb, double* __restrict__ G, const int* __restrict__ skip)
+{
+    __shared__ BbSmem sm;
+    const int m = blockIdx.z / npb, P = blockIdx.z % npb;
+    if (skip && skip[m]) return;
+    const int j0 = P * BB_NB, i0 = j0 + 1;
+    const int rows = min(BB_NB, n - j0);
+    const double* V = Vh + (size_t)m * n * n + (size_t)j0 * n + i0;
+    double acc[2][4][2];
+    BB_ZERO_ACC(acc);
+    bb_gemm_tile<true>(V, n, V, n, rows, rows, n - i0, blockIdx.y * BB_T, blockIdx.x * BB_T, acc, sm);
+    bb_store_tile<false>(G + (size_t)blockIdx.z * BB_NB * BB_NB, BB_NB, BB_NB, BB_NB, blockIdx.y * BB_T, blockIdx.x * BB_T, acc);
+}
+
+// X_P (lower triangular, = T^T of the block): one thread per row a, rows are independent.  grid (npb, M), 128 threads
+__global__ void __launch_bounds__(BB_NB)
+bb_x_kernel(const double* __restrict__ G, const double* __restrict__ tau, int n, int npb, double* __restrict__ X,
+            const int* __restrict__ skip)
+{
+    extern __shared__ double xs[];                   // [BB_NB][BB_NB + 1]
+    const int m = blockIdx.y, P = blockIdx.x;
+    if (skip && skip[m]) return;
+    const int j0 = P * BB_NB, a = threadIdx.x;
+    const double* Gp = G + ((size_t)m * npb + P) * BB_NB * BB_NB;
+    const double* tp = tau + (size_t)m * n + j0;
+    double* xr = xs + (size_t)a * (BB_NB + 1);
+    const double ta = (j0 + a < n - 1) ? tp[a] : 0.0;
+    for (int i = a + 1; i < BB_NB; ++i) xr[i] = 0.0;
+    xr[a] = ta;
+    for (int i = a - 1; i >= 0; --i) {
+        const double* gi = Gp + (size_t)i * BB_NB;   // G is symmetric: row i, contiguous in q
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int q = i + 1;
+        for (; q + 4 <= a + 1; q += 4) {
+            s0 = fma(xr[q], gi[q], s0);
+            s1 = fma(xr[q + 1], gi[q + 1], s1);
+            s2 = fma(xr[q + 2], gi[q + 2], s2);
+            s3 = fma(xr[q + 3], gi[q + 3], s3);
+        }
+        for (; q <= a; ++q) s0 = fma(xr[q], gi[q], s0);
+        const double ti = (j0 + i < n - 1) ? tp[i] : 0.0;
+        xr[i] = -ti * ((s0 + s1) + (s2 + s3));
+    }
+    __syncthreads();
+    double* Xp = X + ((size_t)m * npb + P) * BB_NB * BB_NB;
+    for (int idx = threadIdx.x; idx < BB_NB * BB_NB; idx += BB_NB)
+        Xp[idx] = xs[(size_t)(idx / BB_NB) * (BB_NB + 1) + idx % BB_NB];
+}
+
+// V'_P = X_P V_P  (rows j0..j0+127 of Vp, columns >= j0+1).  grid (ceil(n/64), 2, M*npb)
+__global__ void __launch_bounds__(256)
+bb_vprime_kernel(const double* __restrict__ Vh, const double* __restrict__ X, int n, int npb, double* __restrict__ Vp,
+                 const int* __restrict__ skip)
+{
+    __shared__ BbSmem sm;
+    const int m = blockIdx.z / npb, P = blockIdx.z % npb;
+    if (skip && skip[m]) return;
+    const int j0 = P * BB_NB, i0 = j0 + 1, len = n - i0;
+    const int c0 = blockIdx.x * BB_T, r0 = blockIdx.y * BB_T;
+    if (c0 >= len) return;
+    const int rows = min(BB_NB, n - j0);
+    double acc[2][4][2];
+    BB_ZERO_ACC(acc);
+    bb_gemm_tile<false>(X + (size_t)blockIdx.z * BB_NB * BB_NB, BB_NB, Vh + (size_t)m * n * n + (size_t)j0 * n + i0, n,
+                        rows, len, rows, r0, c0, acc, sm);
+    bb_store_tile<false>(Vp + (size_t)m * n * n + (size_t)j0 * n + i0, n, rows, len, r0, c0, acc);
+}
+
+// Y = Vt[:, i0:] V_P^T   (n x 128).  grid (2, ceil(n/64), M)
+__global__ void __launch_bounds__(256)
+bb_y_kernel(const double* __restrict__ Q, const double* __restrict__ Vh, int n, int P, double* __restrict__ Y,
+            const int* __restrict__ skip)
+{
+    __shared__ BbSmem sm;
+    const int m = blockIdx.z;
+    if (skip && skip[m]) return;
+    const int j0 = P * BB_NB, i0 = j0 + 1;
+    const int rows = min(BB_NB, n - j0);
+    double acc[2][4][2];
+    BB_ZERO_ACC(acc);
+    bb_gemm_tile<true>(Q + (size_t)m * n * n + i0, n, Vh + (size_t)m * n * n + (size_t)j0 * n + i0, n,
+                       n, rows, n - i0, blockIdx.y * BB_T, blockIdx.x * BB_T, acc, sm);
+    bb_store_tile<false>(Y + (size_t)m * n * BB_NB, BB_NB, n, BB_NB, blockIdx.y * BB_T, blockIdx.x * BB_T, acc);
+}
+
+// Vt[:, i0:] -= Y V'_P.  grid (ceil(len/64), ceil(n/64), M)
+__global__ void __launch_bounds__(256)
+bb_upd_kernel(double* __restrict__ Q, const double* __restrict__ Vp, const double* __restrict__ Y, int n, int P,
+              const int* __restrict__ skip)
+{
+    __shared__ BbSmem sm;
+    const int m = blockIdx.z;
+    if (skip && skip[m]) return;
+    const int j0 = P * BB_NB, i0 = j0 + 1, len = n - i0;
+    const int rows = min(BB_NB, n - j0);
+    double acc[2][4][2];
+    BB_ZERO_ACC(acc);
+    bb_gemm_tile<false>(Y + (size_t)m * n * BB_NB, BB_NB, Vp + (size_t)m * n * n + (size_t)j0 * n + i0, n,
+                        n, len, rows, blockIdx.y * BB_T, blockIdx.x * BB_T, acc, sm);
+    bb_store_tile<true>(Q + (size_t)m * n * n + i0, n, n, len, blockIdx.y * BB_T, blockIdx.x * BB_T, acc);
+}
+
 // ---- small helpers ----------------------------------------------------------------------------
 __global__ void tr_skip_kernel(const double* __restrict__ ctrl, int mpp, int M, int* __restrict__ skip)
 {
@@ -1180,6 +1395,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += al(sizeof(double) * (size_t)M * npanels * BT_NB * BT_NB);
     b += al(sizeof(int) * (size_t)M);                     // skip
     b += al(sizeof(double) * (size_t)M);                  // scale
+    b += 2 * al(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);   // G, X of the blocked back-transformation
     return b;
 }
 
@@ -1221,6 +1437,9 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     double* Tm = (double*)take(sizeof(double) * (size_t)M * (npanels + 1) * BT_NB * BT_NB);
     int* skip = (int*)take(sizeof(int) * (size_t)M);
     double* scale = (double*)take(sizeof(double) * (size_t)M);
+    const int npb = (n - 1 + BB_NB - 1) / BB_NB;
+    double* Gb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
+    double* Xb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
     static int stop_after = -1;
     if (stop_after < 0) { const char* ev = getenv("GG_TR_STOP"); stop_after = ev ? atoi(ev) : 0; }
 
@@ -1329,7 +1548,28 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     if (stop_after == 2) return 0;
 
     // ---- stage 3 ----
-    if (npanels > 0 && which != 4) {
+    static int bt_big = -1;
+    if (bt_big < 0) {
+        const char* ev = getenv("GG_BT_BIG");
+        bt_big = ev ? atoi(ev) : 1;
+        cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
+    }
+    if (npanels > 0 && which != 4 && bt_big && n >= BB_MIN) {
+        // U (Delta matrices) and Q0 (D&C ping-pong buffer) are free now: Y lives in U, V' = X V in Q0
+        double* Yb = dw.U;
+        double* Vp = Q0;
+        const int nt64 = (n + BB_T - 1) / BB_T;
+        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, n, npb, Gb, skip);
+        bb_x_kernel<<<dim3(npb, M), BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), s>>>(Gb, tw.tau, n, npb, Xb, skip);
+        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, Xb, n, npb, Vp, skip);
+        GG_CHECK_LAUNCH();
+        for (int P = npb - 1; P >= 0; --P) {
+            const int len = n - (P * BB_NB + 1);
+            bb_y_kernel<<<dim3(BB_NB / BB_T, nt64, M), 256, 0, s>>>(A, tw.Vh, n, P, Yb, skip);
+            bb_upd_kernel<<<dim3((len + BB_T - 1) / BB_T, nt64, M), 256, 0, s>>>(A, Vp, Yb, n, P, skip);
+        }
+    } else if (npanels > 0 && which != 4) {
         bt_larft_kernel<<<dim3(npanels, M), 256, 0, s>>>(tw.Vh, tw.tau, n, Tm, npanels, skip);
         bt_apply_kernel<<<dim3((n + BT_R - 1) / BT_R, M), 256, 0, s>>>(A, tw.Vh, Tm, n, npanels, skip);
     }
