@@ -744,12 +744,27 @@ dc_secular_kernel(int n, int level, double* __restrict__ lam_out, DcWs ws, const
         double lb, ub;
         int ia, ib;
         if (!last) {
-            const double mid = 0.5 * (sdl[j + 1] - sdl[j]);
-            double f = 0.0;
-            for (int i = lane; i < k; i += 32) f += sw2[i] / ((sdl[i] - sdl[j]) - mid);
-            f = 1.0 + gg_warp_sum(f);
-            if (f >= 0.0) { org = j; lb = 0.0; ub = mid; tau = 0.5 * mid; }
-            else { org = j + 1; lb = -mid; ub = 0.0; tau = -0.5 * mid; }
+            const double delta = sdl[j + 1] - sdl[j], mid = 0.5 * delta;
+            double rest = 0.0;                       // all poles but the two that bracket the root, at the midpoint
+            for (int i = lane; i < k; i += 32)
+                if (i != j && i != j + 1) rest += sw2[i] / ((sdl[i] - sdl[j]) - mid);
+            const double c0 = 1.0 + gg_warp_sum(rest);
+            const double wj = sw2[j], wj1 = sw2[j + 1];
+            const double f = c0 + (wj1 - wj) / mid;
+            // initial guess as in dlaed4: keep the two bracketing poles exact, freeze the rest at its midpoint value,
+            // and take the root of the resulting quadratic on the side of the origin
+            if (f >= 0.0) {
+                org = j; lb = 0.0; ub = mid;
+                const double a = c0 * delta + wj + wj1, b = wj * delta;
+                const double sq = sqrt(fabs(a * a - 4.0 * b * c0));
+                tau = (a > 0.0) ? 2.0 * b / (a + sq) : (a - sq) / (2.0 * c0);
+            } else {
+                org = j + 1; lb = -mid; ub = 0.0;
+                const double a = -c0 * delta + wj + wj1, b = wj1 * delta;
+                const double sq = sqrt(fabs(a * a + 4.0 * b * c0));
+                tau = (a > 0.0) ? -2.0 * b / (a + sq) : (a - sq) / (2.0 * c0);   // the negative root of c0 t^2 - a t - b
+            }
+            if (!(tau > lb && tau < ub)) tau = 0.5 * (lb + ub);      // also catches NaN
             ia = j; ib = j + 1;
         } else {
             double span = 0.0;
@@ -1396,6 +1411,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += al(sizeof(int) * (size_t)M);                     // skip
     b += al(sizeof(double) * (size_t)M);                  // scale
     b += 2 * al(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);   // G, X of the blocked back-transformation
+    if (n >= BB_MIN) b += al(sizeof(double) * M * nn);   // V' = X V (formed on a side stream while the D&C stage runs)
     return b;
 }
 
@@ -1440,6 +1456,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     const int npb = (n - 1 + BB_NB - 1) / BB_NB;
     double* Gb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
     double* Xb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
+    double* Vp = (n >= BB_MIN) ? (double*)take(sizeof(double) * M * nn) : nullptr;
     static int stop_after = -1;
     if (stop_after < 0) { const char* ev = getenv("GG_TR_STOP"); stop_after = ev ? atoi(ev) : 0; }
 
@@ -1509,6 +1526,38 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     GG_CHECK_LAUNCH();
     if (stop_after == 1 || (which != 0 && which != 4)) return 0;
 
+    // ---- stage 3 preparation (independent of stage 2): G, X, V' of the blocked back-transformation are formed on a
+    // side stream while the latency-bound divide & conquer kernels run on the caller's stream
+    static int bt_big = -1;
+    static thread_local cudaStream_t side[16] = {};
+    static thread_local cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
+    if (bt_big < 0) {
+        const char* ev = getenv("GG_BT_BIG");
+        bt_big = ev ? atoi(ev) : 1;
+        cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
+    }
+    const bool use_big = npanels > 0 && which != 4 && bt_big && n >= BB_MIN;
+    int dev = 0;
+    if (use_big) {
+        cudaGetDevice(&dev);
+        dev &= 15;
+        if (!side[dev]) {
+            cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming);
+        }
+        cudaStream_t ss = side[dev];
+        cudaEventRecord(ev_fork[dev], s);
+        cudaStreamWaitEvent(ss, ev_fork[dev], 0);
+        const int nt64 = (n + BB_T - 1) / BB_T;
+        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, ss>>>(tw.Vh, n, npb, Gb, skip);
+        bb_x_kernel<<<dim3(npb, M), BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), ss>>>(Gb, tw.tau, n, npb, Xb, skip);
+        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, ss>>>(tw.Vh, Xb, n, npb, Vp, skip);
+        cudaEventRecord(ev_join[dev], ss);
+        GG_CHECK_LAUNCH();
+    }
+
     // ---- stage 2 ----
     // buffers: leaves write Qt into buf[L & 1 ? ...]; arrange so that the root lands in A.
     double* qbuf[2] = {A, Q0};           // level l merge reads qbuf[(l+1)&1], writes qbuf[l&1]; root (l=0) -> A
@@ -1545,25 +1594,14 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     }
     // eigenvalues of the root are in lam[0]; eigenvectors of T (rows) in A
     dc_unscale_kernel<<<dim3(4, M), 256, 0, s>>>(dw.lam[0], scale, n, D, skip);
+    if (use_big) cudaStreamWaitEvent(s, ev_join[dev], 0);      // join the stage-3 preparation
     if (stop_after == 2) return 0;
 
     // ---- stage 3 ----
-    static int bt_big = -1;
-    if (bt_big < 0) {
-        const char* ev = getenv("GG_BT_BIG");
-        bt_big = ev ? atoi(ev) : 1;
-        cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
-    }
-    if (npanels > 0 && which != 4 && bt_big && n >= BB_MIN) {
-        // U (Delta matrices) and Q0 (D&C ping-pong buffer) are free now: Y lives in U, V' = X V in Q0
+    if (use_big) {
+        // U (Delta matrices of the D&C stage) is free now: Y lives there
         double* Yb = dw.U;
-        double* Vp = Q0;
         const int nt64 = (n + BB_T - 1) / BB_T;
-        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, n, npb, Gb, skip);
-        bb_x_kernel<<<dim3(npb, M), BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), s>>>(Gb, tw.tau, n, npb, Xb, skip);
-        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, Xb, n, npb, Vp, skip);
-        GG_CHECK_LAUNCH();
         for (int P = npb - 1; P >= 0; --P) {
             const int len = n - (P * BB_NB + 1);
             bb_y_kernel<<<dim3(BB_NB / BB_T, nt64, M), 256, 0, s>>>(A, tw.Vh, n, P, Yb, skip);
