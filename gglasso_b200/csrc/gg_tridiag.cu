@@ -208,21 +208,172 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
 // updates kb..j-1 (a_rc -= v_k[r] w_k[c] + w_k[r] v_k[c]) in registers, stores the tile only on a write pass, and
 // accumulates the full symmetric y = A v from that single pass: y_I += T v_J (row sums) and, mirrored,
 // y_J += T^T v_I (column sums; strictly upper part on diagonal tiles).  Each thread owns a 4 x 4 register block
-// (rows 4*ty+i, columns tx+16*jj: a half warp reads 128 contiguous bytes of a row); the tile loads are issued before
-// anything else, the row sums are reduced with shuffles over the 16 lanes of a half warp and the column sums over
-// the 16 row groups through a small shared array.  128 FP64 atomics per tile.
+// (rows 4*ty+i, columns tx+16*jj: a half warp reads 128 contiguous bytes of a row); every global load of the CTA is
+// issued before anything is consumed; partial sums go through shared memory, so the 128 FP64 atomics of a tile
+// are four coalesced warp instructions.
+// The kernel is instruction-issue bound (ncu: 55-66 % issue slots busy, FP64 pipe 15 %, DRAM 30 %), so the body is
+// compiled twice: INTERIOR tiles (strictly above the diagonal and fully inside the block -- most of them) carry no
+// bounds predicates, no masks and no selects.
 #define SV_T 64
+struct SvSmem {
+    __align__(16) double vp[TR_QMAX][2][SV_T];
+    __align__(16) double w[TR_QMAX][2][SV_T];
+    __align__(16) double vI[SV_T];
+    __align__(16) double vJ[SV_T];
+    double rowp[SV_T][17];                       // [row][tx] partial row sums (stride 17: conflict-free read-back)
+    double colp[16][SV_T];                       // [ty][col] partial column sums
+};
+
+template <bool INTERIOR>
+__device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int j, int kb, int write, const TrWs& ws,
+                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm)
+{
+    const int t = n - j - 1, base = j + 1, cnt = j - kb;
+#ifdef TR_TIMING
+    const bool tr_stamp_on = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+#endif
+    const int sk = skip ? skip[m] : 0;
+    const int r0 = I * SV_T, c0 = J * SV_T;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int rb = r0 + 4 * ty, cb = c0 + tx;
+    double* Am = A + (size_t)m * n * n + (size_t)base * n + base;
+    double* pt = Am + (size_t)rb * n + cb;        // element (i, jj) of the register block: pt[i*n + 16*jj]
+    double a[4][4];
+    unsigned okm = 0xffffu;
+    if (INTERIOR) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) a[i][jj] = pt[(size_t)i * n + 16 * jj];
+    } else {
+        okm = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int r = rb + i, c = cb + 16 * jj;
+                const bool ok = (r < t && c < t && c >= r);
+                okm |= ok ? (1u << (4 * i + jj)) : 0u;
+                a[i][jj] = ok ? pt[(size_t)i * n + 16 * jj] : 0.0;
+            }
+    }
+    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
+    const double* wring = ws.w + (size_t)m * TR_QMAX * n + base;
+    const double* Vhm = ws.Vh + (size_t)m * n * n + base;
+    double pv[2], pw[2], cv = 0.0;            // staged element e = tid + 256 u: pair q = e/128, half h, lane l
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int e = tid + 256 * u;
+        const int q = e >> 7, h = (e >> 6) & 1, l = e & 63, k = kb + q;
+        const int pos = (h ? c0 : r0) + l;
+        const bool ok = (q < cnt) && (INTERIOR || pos < t);
+        pv[u] = ok ? Vhm[(size_t)k * n + pos] : 0.0;
+        pw[u] = ok ? wring[(size_t)(k % TR_QMAX) * n + pos] : 0.0;
+    }
+    if (tid < 2 * SV_T) {
+        const int pos = (tid < SV_T) ? r0 + tid : c0 + tid - SV_T;
+        cv = (INTERIOR || pos < t) ? vcur[pos] : 0.0;
+    }
+    if (sk) return;                           // (block-uniform; no barrier has been passed yet)
+    TR_STAMP(1, 2);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int e = tid + 256 * u;
+        (&sm.vp[0][0][0])[e] = pv[u];
+        (&sm.w[0][0][0])[e] = pw[u];
+    }
+    if (tid < SV_T) sm.vI[tid] = cv;
+    else if (tid < 2 * SV_T) sm.vJ[tid - SV_T] = cv;
+    __syncthreads();
+    TR_STAMP(1, 3);
+    // pending updates, oldest first.  Out-of-range rows / columns carry zeros in the staged vectors, so only the
+    // lower part of a diagonal tile has to be masked afterwards (it must stay zero for the sums below).
+    for (int k = 0; k < cnt; ++k) {
+        double wc[4], vc[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { wc[jj] = sm.w[k][1][tx + 16 * jj]; vc[jj] = sm.vp[k][1][tx + 16 * jj]; }
+        const double2 v01 = *reinterpret_cast<const double2*>(&sm.vp[k][0][4 * ty]);
+        const double2 v23 = *reinterpret_cast<const double2*>(&sm.vp[k][0][4 * ty + 2]);
+        const double2 w01 = *reinterpret_cast<const double2*>(&sm.w[k][0][4 * ty]);
+        const double2 w23 = *reinterpret_cast<const double2*>(&sm.w[k][0][4 * ty + 2]);
+        const double vr[4] = {v01.x, v01.y, v23.x, v23.y}, wr[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) a[i][jj] = a[i][jj] - vr[i] * wc[jj] - wr[i] * vc[jj];
+    }
+    if (!INTERIOR) {
+        if (I == J && cnt > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    if (!(okm & (1u << (4 * i + jj)))) a[i][jj] = 0.0;
+        }
+    }
+    if (write) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (INTERIOR || (okm & (1u << (4 * i + jj)))) pt[(size_t)i * n + 16 * jj] = a[i][jj];
+    }
+#ifdef TR_TIMING
+    if (a[0][0] == 1.2345e300) return;       // (forces the tile loads to have landed before the stamp)
+#endif
+    TR_STAMP(1, 4);
+    {
+        double vJ[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vJ[q] = sm.vJ[tx + 16 * q];
+        const double2 i01 = *reinterpret_cast<const double2*>(&sm.vI[4 * ty]);
+        const double2 i23 = *reinterpret_cast<const double2*>(&sm.vI[4 * ty + 2]);
+        const double vI[4] = {i01.x, i01.y, i23.x, i23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) sacc = fma(a[i][jj], vJ[jj], sacc);
+            sm.rowp[4 * ty + i][tx] = sacc;              // includes the diagonal
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool dg = !INTERIOR && (I == J) && (rb + i == cb + 16 * jj);   // mirrored part: strictly upper
+                sacc = fma(dg ? 0.0 : a[i][jj], vI[i], sacc);
+            }
+            sm.colp[ty][tx + 16 * jj] = sacc;
+        }
+    }
+    __syncthreads();
+    TR_STAMP(1, 5);
+    double* y = ws.y + (size_t)m * n + base;
+    if (tid < SV_T) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) { s0 += sm.rowp[tid][q]; s1 += sm.rowp[tid][q + 1]; }
+        if (INTERIOR || r0 + tid < t) atomicAdd(y + r0 + tid, s0 + s1);
+    } else if (tid < 2 * SV_T) {
+        const int cc = tid - SV_T;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) { s0 += sm.colp[q][cc]; s1 += sm.colp[q + 1][cc]; }
+        if (INTERIOR || c0 + cc < t) atomicAdd(y + c0 + cc, s0 + s1);
+    }
+    TR_STAMP(1, 6);
+}
+
 __global__ void __launch_bounds__(256, 3)
 tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt)
 {
-    __shared__ double s_vp[TR_QMAX][2][SV_T], s_w[TR_QMAX][2][SV_T], s_vI[SV_T], s_vJ[SV_T], s_col[8][SV_T], s_row[SV_T];
+    __shared__ SvSmem sm;
     // Boustrophedon sweep: consecutive launches walk the (matrix, tile) space in opposite directions, so a launch
     // starts with the tiles the previous one touched last -- they are still in L2 (an identical sweep order is the
     // worst case for an LRU-like cache when the ~80 MB working set exceeds the usable capacity).
     const bool rev = (j & 1) != 0;
     const int m = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-    const int t = n - j - 1;
-    const int base = j + 1;
     int idx = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, I = 0;
     while (idx >= nt - I) { idx -= nt - I; ++I; }
     const int J = I + idx;
@@ -233,133 +384,9 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
     TR_STAMP(1, 1);
-    // Every global load of the CTA is issued here, back to back, before anything is consumed: the skip flag, the
-    // 4 x 4 register block of the tile and the slices of the pending / current vectors (one round trip in total).
-    const int sk = skip ? skip[m] : 0;
-    const int r0 = I * SV_T, c0 = J * SV_T;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int rb = r0 + 4 * ty, cb = c0 + tx;
-    double* Am = A + (size_t)m * n * n + (size_t)base * n + base;
-    double a[4][4];
-    unsigned okm = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int r = rb + i, c = cb + 16 * jj;
-            const bool ok = (r < t && c < t && c >= r);
-            okm |= ok ? (1u << (4 * i + jj)) : 0u;
-            a[i][jj] = ok ? Am[(size_t)r * n + c] : 0.0;
-        }
-    const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
-    const double* wring = ws.w + (size_t)m * TR_QMAX * n + base;
-    const double* Vhm = ws.Vh + (size_t)m * n * n + base;
-    const int cnt = j - kb;
-    double pv[2], pw[2], cv = 0.0;            // staged element e = tid + 256 u: pair q = e/128, half h, lane l
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int e = tid + 256 * u;
-        const int q = e >> 7, h = (e >> 6) & 1, l = e & 63, k = kb + q;
-        const int pos = (h ? c0 : r0) + l;
-        const bool ok = (q < cnt) && (pos < t);
-        pv[u] = ok ? Vhm[(size_t)k * n + pos] : 0.0;
-        pw[u] = ok ? wring[(size_t)(k % TR_QMAX) * n + pos] : 0.0;
-    }
-    if (tid < 2 * SV_T) {
-        const int pos = (tid < SV_T) ? r0 + tid : c0 + tid - SV_T;
-        cv = (pos < t) ? vcur[pos] : 0.0;
-    }
-    if (sk) return;                           // (block-uniform; no barrier has been passed yet)
-    TR_STAMP(1, 2);
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int e = tid + 256 * u;
-        (&s_vp[0][0][0])[e] = pv[u];
-        (&s_w[0][0][0])[e] = pw[u];
-    }
-    if (tid < SV_T) s_vI[tid] = cv;
-    else if (tid < 2 * SV_T) s_vJ[tid - SV_T] = cv;
-    __syncthreads();
-    TR_STAMP(1, 3);
-    // pending updates, oldest first.  Out-of-range rows / columns carry zeros in the staged vectors, so only the
-    // lower part of a diagonal tile has to be masked (it must stay zero for the sums below).
-    for (int k = 0; k < cnt; ++k) {
-        double wc[4], vc[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) { wc[jj] = s_w[k][1][tx + 16 * jj]; vc[jj] = s_vp[k][1][tx + 16 * jj]; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double vr = s_vp[k][0][4 * ty + i], wr = s_w[k][0][4 * ty + i];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) a[i][jj] = a[i][jj] - vr * wc[jj] - wr * vc[jj];
-        }
-    }
-    if (I == J && cnt > 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                if (!(okm & (1u << (4 * i + jj)))) a[i][jj] = 0.0;
-    }
-    if (write) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                if (okm & (1u << (4 * i + jj))) Am[(size_t)(rb + i) * n + cb + 16 * jj] = a[i][jj];
-    }
-#ifdef TR_TIMING
-    if (a[0][0] == 1.2345e300) return;       // (forces the tile loads to have landed before the stamp)
-#endif
-    TR_STAMP(1, 4);
-    double vJ[4], vI[4], row[4], col[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { vJ[q] = s_vJ[tx + 16 * q]; vI[q] = s_vI[4 * ty + q]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) s = fma(a[i][jj], vJ[jj], s);
-        row[i] = s;                                      // includes the diagonal
-    }
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool dg = (I == J) && (rb + i == cb + 16 * jj);   // mirrored part: strictly upper only
-            s = fma(dg ? 0.0 : a[i][jj], vI[i], s);
-        }
-        col[jj] = s;
-    }
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) row[i] += __shfl_xor_sync(0xffffffffu, row[i], o);
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) col[jj] += __shfl_xor_sync(0xffffffffu, col[jj], 16);
-    // stage both partial results so that the 128 atomics of the tile are four fully coalesced warp instructions
-    if (tx == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s_row[4 * ty + i] = row[i];
-    }
-    if ((tid & 16) == 0) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) s_col[tid >> 5][tx + 16 * jj] = col[jj];
-    }
-    __syncthreads();
-    TR_STAMP(1, 5);
-    double* y = ws.y + (size_t)m * n + base;
-    if (tid < SV_T) {
-        if (r0 + tid < t) atomicAdd(y + r0 + tid, s_row[tid]);
-    } else if (tid < 2 * SV_T) {
-        const int cc = tid - SV_T;
-        double s = 0.0;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) s += s_col[w8][cc];
-        if (c0 + cc < t) atomicAdd(y + c0 + cc, s);
-    }
-    TR_STAMP(1, 6);
+    const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
+    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm);
+    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm);
 }
 
 // Tail of the tridiagonalisation: once the trailing block has at most TR_TAIL rows it fits in shared memory, and
