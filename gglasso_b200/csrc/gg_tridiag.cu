@@ -365,7 +365,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
     TR_STAMP(1, 6);
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt)
 {
     __shared__ SvSmem sm;
