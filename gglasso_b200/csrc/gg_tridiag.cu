@@ -96,8 +96,10 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
     const bool tr_stamp_on = (blockIdx.x == 0 && threadIdx.x == 0);
 #endif
     TR_STAMP(0, 0);
-    asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
+    // Wait for the previous tr_symv_kernel first and only then release the next one: its CTAs start loading their
+    // tiles of A before their own wait, which is safe exactly because the last writer of A has completed here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     TR_STAMP(0, 1);
     const int sk = skip ? skip[m] : 0;        // consumed below, after the other loads have been issued
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -232,19 +234,21 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
 #ifdef TR_TIMING
     const bool tr_stamp_on = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
 #endif
-    const int sk = skip ? skip[m] : 0;
     const int r0 = I * SV_T, c0 = J * SV_T;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int rb = r0 + 4 * ty, cb = c0 + tx;
     double* Am = A + (size_t)m * n * n + (size_t)base * n + base;
     double* pt = Am + (size_t)rb * n + cb;        // element (i, jj) of the register block: pt[i*n + 16*jj]
+    // The tile is loaded BEFORE griddepcontrol.wait: A is written only by tr_symv_kernel launches, and the previous
+    // one had completed before the column kernel in between released this grid (see tr_col_kernel), so these loads
+    // overlap the column step.  ld.global.cg: straight from L2 -- no reuse, and no stale L1 lines across launches.
     double a[4][4];
     unsigned okm = 0xffffu;
     if (INTERIOR) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) a[i][jj] = pt[(size_t)i * n + 16 * jj];
+            for (int jj = 0; jj < 4; ++jj) a[i][jj] = __ldcg(pt + (size_t)i * n + 16 * jj);
     } else {
         okm = 0;
 #pragma unroll
@@ -254,9 +258,12 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
                 const int r = rb + i, c = cb + 16 * jj;
                 const bool ok = (r < t && c < t && c >= r);
                 okm |= ok ? (1u << (4 * i + jj)) : 0u;
-                a[i][jj] = ok ? pt[(size_t)i * n + 16 * jj] : 0.0;
+                a[i][jj] = ok ? __ldcg(pt + (size_t)i * n + 16 * jj) : 0.0;
             }
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything below reads what the column kernel wrote
+    TR_STAMP(1, 1);
+    const int sk = skip ? skip[m] : 0;
     const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
     const double* wring = ws.w + (size_t)m * TR_QMAX * n + base;
     const double* Vhm = ws.Vh + (size_t)m * n * n + base;
@@ -382,8 +389,6 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
 #endif
     TR_STAMP(1, 0);
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // ... and wait here until the prior grid has completed
-    TR_STAMP(1, 1);
     const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
     if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm);
     else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm);
