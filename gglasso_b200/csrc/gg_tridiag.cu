@@ -523,6 +523,19 @@ struct DcWs {
     int nodes_max;
 };
 
+// Reciprocal for the secular equation: hardware seed (about 20 bits) plus two Newton steps, no special-case
+// handling -- about 6 instructions instead of the ~35 of an IEEE division, and dc_secular_kernel is bound by
+// exactly that instruction count.  Accurate to an ulp or two, which the stopping test's rounding bound
+// (8 sum|t| eps) covers; the pole distances that define the eigenvectors are formed without any division.
+__device__ __forceinline__ double dc_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 __host__ __device__ __forceinline__ int dc_bnd(int n, int level, int i) { return (int)(((long long)i * n) >> level); }
 
 // normalise T to unit max-norm (as dstedc does) so the deflation tolerance is scale free
@@ -734,11 +747,20 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
         ws.wnd[(size_t)m * n + lo + i] = sz[nd[i]];
     }
     // deflated eigenpairs go to rows lo+k.. of the output unchanged
-    for (int t = 0; t < ndf; ++t) {
+    // (one warp per row, four independent loads in flight per lane: the rows are independent copies)
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    for (int t = wid; t < ndf; t += nw) {
         const double* src = Qm + (size_t)(lo + df[t]) * n + lo;
         double* dst = Qo + (size_t)(lo + k + t) * n + lo;
-        for (int col = tid; col < N; col += nt) dst[col] = src[col];
-        if (tid == 0) lam_out[(size_t)m * n + lo + k + t] = sd[df[t]];
+        for (int col = lane; col < N; col += 128) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (col + 32 * u < N) ? src[col + 32 * u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (col + 32 * u < N) dst[col + 32 * u] = v[u];
+        }
+        if (lane == 0) lam_out[(size_t)m * n + lo + k + t] = sd[df[t]];
     }
 }
 
@@ -779,7 +801,7 @@ dc_secular_kernel(int n, int level, double* __restrict__ lam_out, DcWs ws, const
             const double delta = sdl[j + 1] - sdl[j], mid = 0.5 * delta;
             double rest = 0.0;                       // all poles but the two that bracket the root, at the midpoint
             for (int i = lane; i < k; i += 32)
-                if (i != j && i != j + 1) rest += sw2[i] / ((sdl[i] - sdl[j]) - mid);
+                if (i != j && i != j + 1) rest += sw2[i] * dc_rcp((sdl[i] - sdl[j]) - mid);
             const double c0 = 1.0 + gg_warp_sum(rest);
             const double wj = sw2[j], wj1 = sw2[j + 1];
             const double f = c0 + (wj1 - wj) / mid;
@@ -809,7 +831,7 @@ dc_secular_kernel(int n, int level, double* __restrict__ lam_out, DcWs ws, const
         for (int it = 0; it < 100; ++it) {
             double psi = 0.0, phi = 0.0, dpsi = 0.0, dphi = 0.0, sabs = 0.0;
             for (int i = lane; i < k; i += 32) {
-                const double rcp = 1.0 / ((sdl[i] - dorg) - tau);      // one division per term
+                const double rcp = dc_rcp((sdl[i] - dorg) - tau);      // one reciprocal per term
                 const double t = sw2[i] * rcp;
                 const double dt = t * rcp;
                 if (i < split) { psi += t; dpsi += dt; } else { phi += t; dphi += dt; }
