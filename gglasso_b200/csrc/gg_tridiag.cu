@@ -518,6 +518,9 @@ struct DcWs {
     int* rotp;        // (M,n)
     int* rotn;        // (M,n)
     int* nodek;       // (M,nodes_max) number of non-deflated
+    int* nodeka;      // (M,nodes_max,2) lengths of the two per-child K lists below
+    int* lista;       // (M,n) non-deflated poles whose row of Qt has entries in the first child's columns
+    int* listb;       // (M,n) ... in the second child's columns (rows mixed by a Givens deflation are in both)
     double* noderho;  // (M,nodes_max)
     double* U;        // (M,n,n) Delta / eigenvector matrices, block diagonal like Qt
     int nodes_max;
@@ -661,6 +664,7 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
     int* idx = (int*)(sm + 2 * N);
     int* nd = idx + N;
     int* df = nd + N;
+    unsigned char* typ = (unsigned char*)(df + N);   // 1: first child, 3: second child, 2: mixed by a rotation
     double* rc = ws.rotc + (size_t)m * n + lo;  // rotation lists live in global memory (only thread 0 writes)
     double* rs = ws.rots + (size_t)m * n + lo;
     int* rp = ws.rotp + (size_t)m * n + lo;
@@ -677,6 +681,7 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
     for (int i = tid; i < N; i += nt) {
         sd[i] = lam_in[(size_t)m * n + lo + i];
         sz[i] = (i < n1 ? Qm[(size_t)(lo + i) * n + mid - 1] : sgn * Qm[(size_t)(lo + i) * n + mid]) * isq2;
+        typ[i] = (i < n1) ? 1 : 3;
     }
     __syncthreads();
     // rank sort (stable)
@@ -714,6 +719,7 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
                     sd[nj] = sd[pj] * s * s + sd[nj] * c * c;
                     sd[pj] = tnew;
                     df[ndf++] = pj;
+                    if (typ[pj] != typ[nj]) typ[nj] = 2;
                     pj = nj;
                 } else {
                     nd[k++] = pj;
@@ -722,6 +728,18 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
             }
             if (pj >= 0) nd[k++] = pj;
         }
+        // The rows of Qt are block diagonal (each child's eigenvectors live in its own columns), so the basis update
+        // of a column range only needs the poles whose row has entries there: two K lists, as dlaed3's coltyp split
+        int ka = 0, kb = 0;
+        int* la = ws.lista + (size_t)m * n + lo;
+        int* lb = ws.listb + (size_t)m * n + lo;
+        for (int i = 0; i < k; ++i) {
+            const int ty = typ[nd[i]];
+            if (ty != 3) la[ka++] = i;
+            if (ty != 1) lb[kb++] = i;
+        }
+        ws.nodeka[((size_t)m * ws.nodes_max + node) * 2] = ka;
+        ws.nodeka[((size_t)m * ws.nodes_max + node) * 2 + 1] = kb;
         s_k = k; s_ndf = ndf; s_nrot = nrot; s_rho = rho;
         ws.nodek[(size_t)m * ws.nodes_max + node] = k;
         ws.noderho[(size_t)m * ws.nodes_max + node] = rho;
@@ -965,21 +983,37 @@ dc_gemm_kernel(int n, int level, const double* __restrict__ Qin, double* __restr
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
     const int wr = wid >> 1, wc = wid & 1;          // 4 x 2 warps, 16 x 32 outputs each
-    const int nchunks = (k + DG_KC - 1) / DG_KC;
+    // K list of this column tile: first child's columns / second child's columns / all poles for the one tile that
+    // straddles the split (klist == nullptr: identity)
+    const int n1 = dc_bnd(n, level + 1, 2 * node + 1) - lo;
+    const int* klist = nullptr;
+    int kk = k;
+    if (c0 + DG_T <= n1) {
+        klist = ws.lista + (size_t)m * n + lo;
+        kk = ws.nodeka[((size_t)m * ws.nodes_max + node) * 2];
+    } else if (c0 >= n1) {
+        klist = ws.listb + (size_t)m * n + lo;
+        kk = ws.nodeka[((size_t)m * ws.nodes_max + node) * 2 + 1];
+    }
+    const int nchunks = (kk + DG_KC - 1) / DG_KC;
 
     auto load_chunk = [&](int ch, int buf) {
         const int i0 = ch * DG_KC;
         for (int idx = tid; idx < DG_T * DG_KC; idx += 256) {
             const int jj = idx / DG_KC, ii = idx % DG_KC;
             double* dst = &As[buf][jj][ii];
-            if (j0 + jj < k && i0 + ii < k) gg_cp_async8(dst, Um + (size_t)(j0 + jj) * n + i0 + ii);
-            else *dst = 0.0;
+            if (j0 + jj < k && i0 + ii < kk) {
+                const int ip = klist ? klist[i0 + ii] : i0 + ii;
+                gg_cp_async8(dst, Um + (size_t)(j0 + jj) * n + ip);
+            } else *dst = 0.0;
         }
         for (int idx = tid; idx < DG_KC * DG_T; idx += 256) {
             const int ii = idx / DG_T, cc = idx % DG_T;
             double* dst = &Bs[buf][ii][cc];
-            if (i0 + ii < k && c0 + cc < N) gg_cp_async8(dst, Qm + (size_t)ndrow[i0 + ii] * n + lo + c0 + cc);
-            else *dst = 0.0;
+            if (i0 + ii < kk && c0 + cc < N) {
+                const int ip = klist ? klist[i0 + ii] : i0 + ii;
+                gg_cp_async8(dst, Qm + (size_t)ndrow[ip] * n + lo + c0 + cc);
+            } else *dst = 0.0;
         }
         gg_cp_commit();
     };
@@ -1460,6 +1494,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += (2 + TR_QMAX) * al(sizeof(double) * Mn);
     b += 3 * al(sizeof(int) * Mn) + 2 * al(sizeof(double) * Mn);   // ndrow, rotp, rotn, rotc, rots
     b += al(sizeof(int) * (size_t)M * (1 << L));          // nodek
+    b += al(sizeof(int) * (size_t)M * (1 << L) * 2) + 2 * al(sizeof(int) * Mn);   // nodeka, lista, listb
     b += al(sizeof(double) * (size_t)M * (1 << L));       // noderho
     b += al(sizeof(double) * (size_t)M * npanels * BT_NB * BT_NB);
     b += al(sizeof(int) * (size_t)M);                     // skip
@@ -1504,6 +1539,9 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     dw.nodes_max = 1 << L;
     dw.nodek = (int*)take(sizeof(int) * (size_t)M * dw.nodes_max);
     dw.noderho = (double*)take(sizeof(double) * (size_t)M * dw.nodes_max);
+    dw.nodeka = (int*)take(sizeof(int) * (size_t)M * dw.nodes_max * 2);
+    dw.lista = (int*)take(sizeof(int) * Mn);
+    dw.listb = (int*)take(sizeof(int) * Mn);
     double* Tm = (double*)take(sizeof(double) * (size_t)M * (npanels + 1) * BT_NB * BT_NB);
     int* skip = (int*)take(sizeof(int) * (size_t)M);
     double* scale = (double*)take(sizeof(double) * (size_t)M);
@@ -1634,7 +1672,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     for (int l = L - 1; l >= 0; --l) {
         const int nodes = 1 << l;
         const int Nmax = ((n + nodes - 1) >> l) + 1;
-        const size_t psm = sizeof(double) * 2 * Nmax + sizeof(int) * 3 * Nmax + 16;
+        const size_t psm = sizeof(double) * 2 * Nmax + sizeof(int) * 3 * Nmax + Nmax + 16;
         if (psm > 200 * 1024) return -4;
         const double* Qin = qbuf[(l + 1) & 1];
         double* Qout = qbuf[l & 1];
