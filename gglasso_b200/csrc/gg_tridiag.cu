@@ -1347,38 +1347,37 @@ bb_gram_kernel(const double* __restrict__ Vh, int n, int npb, double* __restrict
     bb_store_tile<false>(G + (size_t)blockIdx.z * BB_NB * BB_NB, BB_NB, BB_NB, BB_NB, blockIdx.y * BB_T, blockIdx.x * BB_T, acc);
 }
 
-// X_P (lower triangular, = T^T of the block): one thread per row a, rows are independent.  grid (npb, M), 128 threads
-__global__ void __launch_bounds__(BB_NB)
+// X_P (lower triangular, = T^T of the block): rows are independent; eight lanes share a row (they split the dot
+// product of every recurrence step), four rows per warp.  grid (npb, M), 8 * BB_NB threads
+__global__ void __launch_bounds__(8 * BB_NB)
 bb_x_kernel(const double* __restrict__ G, const double* __restrict__ tau, int n, int npb, double* __restrict__ X,
             const int* __restrict__ skip)
 {
     extern __shared__ double xs[];                   // [BB_NB][BB_NB + 1]
     const int m = blockIdx.y, P = blockIdx.x;
     if (skip && skip[m]) return;
-    const int j0 = P * BB_NB, a = threadIdx.x;
+    const int j0 = P * BB_NB, a = threadIdx.x >> 3, l = threadIdx.x & 7;
+    const int amax = a | 3;                          // last row handled by this warp
     const double* Gp = G + ((size_t)m * npb + P) * BB_NB * BB_NB;
     const double* tp = tau + (size_t)m * n + j0;
     double* xr = xs + (size_t)a * (BB_NB + 1);
-    const double ta = (j0 + a < n - 1) ? tp[a] : 0.0;
-    for (int i = a + 1; i < BB_NB; ++i) xr[i] = 0.0;
-    xr[a] = ta;
-    for (int i = a - 1; i >= 0; --i) {
+    for (int i = a + 1 + l; i < BB_NB; i += 8) xr[i] = 0.0;
+    if (l == 0) xr[a] = (j0 + a < n - 1) ? tp[a] : 0.0;
+    __syncwarp();
+    for (int i = amax - 1; i >= 0; --i) {
         const double* gi = Gp + (size_t)i * BB_NB;   // G is symmetric: row i, contiguous in q
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int q = i + 1;
-        for (; q + 4 <= a + 1; q += 4) {
-            s0 = fma(xr[q], gi[q], s0);
-            s1 = fma(xr[q + 1], gi[q + 1], s1);
-            s2 = fma(xr[q + 2], gi[q + 2], s2);
-            s3 = fma(xr[q + 3], gi[q + 3], s3);
-        }
-        for (; q <= a; ++q) s0 = fma(xr[q], gi[q], s0);
-        const double ti = (j0 + i < n - 1) ? tp[i] : 0.0;
-        xr[i] = -ti * ((s0 + s1) + (s2 + s3));
+        double sacc = 0.0;
+        if (i < a)
+            for (int q = i + 1 + l; q <= a; q += 8) sacc = fma(xr[q], gi[q], sacc);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+        if (i < a && l == 0) xr[i] = -((j0 + i < n - 1) ? tp[i] : 0.0) * sacc;
+        __syncwarp();
     }
     __syncthreads();
     double* Xp = X + ((size_t)m * npb + P) * BB_NB * BB_NB;
-    for (int idx = threadIdx.x; idx < BB_NB * BB_NB; idx += BB_NB)
+    for (int idx = threadIdx.x; idx < BB_NB * BB_NB; idx += 8 * BB_NB)
         Xp[idx] = xs[(size_t)(idx / BB_NB) * (BB_NB + 1) + idx % BB_NB];
 }
 
@@ -1500,7 +1499,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += al(sizeof(int) * (size_t)M);                     // skip
     b += al(sizeof(double) * (size_t)M);                  // scale
     b += 2 * al(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);   // G, X of the blocked back-transformation
-    if (n >= BB_MIN) b += al(sizeof(double) * M * nn);   // V' = X V (formed on a side stream while the D&C stage runs)
+    if (n >= BB_MIN) b += al(sizeof(double) * M * nn);   // V' = X V
     return b;
 }
 
@@ -1618,35 +1617,23 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     GG_CHECK_LAUNCH();
     if (stop_after == 1 || (which != 0 && which != 4)) return 0;
 
-    // ---- stage 3 preparation (independent of stage 2): G, X, V' of the blocked back-transformation are formed on a
-    // side stream while the latency-bound divide & conquer kernels run on the caller's stream
+    // ---- stage 3 preparation: G, X, V' of the blocked back-transformation (independent of stage 2).
+    // (Running these three launches on a side stream next to the divide & conquer kernels gained 0.3 ms at cfg3 but
+    // corrupted results when five host threads drove five solves concurrently -- see DESIGN.md 4.4; they are plain
+    // launches on the caller's stream.)
     static int bt_big = -1;
-    static thread_local cudaStream_t side[16] = {};
-    static thread_local cudaEvent_t ev_fork[16] = {}, ev_join[16] = {};
     if (bt_big < 0) {
         const char* ev = getenv("GG_BT_BIG");
-        bt_big = ev ? atoi(ev) : 1;
         cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
+        bt_big = ev ? atoi(ev) : 1;
     }
     const bool use_big = npanels > 0 && which != 4 && bt_big && n >= BB_MIN;
-    int dev = 0;
     if (use_big) {
-        cudaGetDevice(&dev);
-        dev &= 15;
-        if (!side[dev]) {
-            cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking);
-            cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming);
-        }
-        cudaStream_t ss = side[dev];
-        cudaEventRecord(ev_fork[dev], s);
-        cudaStreamWaitEvent(ss, ev_fork[dev], 0);
         const int nt64 = (n + BB_T - 1) / BB_T;
-        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, ss>>>(tw.Vh, n, npb, Gb, skip);
-        bb_x_kernel<<<dim3(npb, M), BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), ss>>>(Gb, tw.tau, n, npb, Xb, skip);
-        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, ss>>>(tw.Vh, Xb, n, npb, Vp, skip);
-        cudaEventRecord(ev_join[dev], ss);
+        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, n, npb, Gb, skip);
+        bb_x_kernel<<<dim3(npb, M), 8 * BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), s>>>(Gb, tw.tau, n, npb, Xb, skip);
+        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, Xb, n, npb, Vp, skip);
         GG_CHECK_LAUNCH();
     }
 
@@ -1686,7 +1673,6 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     }
     // eigenvalues of the root are in lam[0]; eigenvectors of T (rows) in A
     dc_unscale_kernel<<<dim3(4, M), 256, 0, s>>>(dw.lam[0], scale, n, D, skip);
-    if (use_big) cudaStreamWaitEvent(s, ev_join[dev], 0);      // join the stage-3 preparation
     if (stop_after == 2) return 0;
 
     // ---- stage 3 ----

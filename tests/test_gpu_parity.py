@@ -511,6 +511,26 @@ def test_grid_search_device_resident_matches_host_driver():
     assert _rel(best_s["Theta"], best_d["Theta"]) < PER_ITER_TOL
 
 
+def test_grid_many_concurrent_columns_large_p():
+    """eight columns on eight host threads / CUDA streams at a size that takes the full large-p eigensolver path
+    (p >= 256: lazy-write sytrd with programmatic dependent launch, D&C, blocked back-transformation): the score
+    table, iteration counts and optimum must equal the single-stream run.  (Regression test: a side stream inside
+    gg_eigh once corrupted results only under this kind of load.)"""
+    from gglasso_b200.datagen import synthetic_mgl
+    from gglasso_b200.parallel import grid_search_device
+    K, p = 6, 384
+    S = synthetic_mgl(K, p, N=2 * p, seed=11)
+    l1, l2 = np.logspace(-0.3, -1.7, 8), np.logspace(-1, -2, 2)
+    sc1, it1, ix1, b1 = grid_search_device(S, np.full(K, 2 * p), "GGL", l1, l2, gamma=0.1, tol=1e-6, rtol=1e-6)
+    for rep in range(2):
+        sc8, it8, ix8, b8 = grid_search_device(S, np.full(K, 2 * p), "GGL", l1, l2, gamma=0.1, tol=1e-6, rtol=1e-6,
+                                               n_streams=8)
+        assert np.isfinite(sc8).all()
+        np.testing.assert_allclose(sc8, sc1, rtol=1e-8)
+        assert tuple(ix8) == tuple(ix1) and np.abs(it8 - it1).max() <= 1
+        assert _rel(b8["Theta"], b1["Theta"]) < 1e-6
+
+
 def test_admm_fsgl_vs_reference_golden(golden):
     """functional SGL (block-Frobenius prox) vs the real reference's output, with and without latent variables."""
     from gglasso_b200 import ADMM_FSGL
