@@ -286,7 +286,9 @@ def launches_per_iter(p, K, sweeps):
     levels = 0
     while ((p + (1 << levels) - 1) >> levels) > 32:
         levels += 1
-    eigh = 5 + (2 * p - 1) + 4 + 5 * levels + 1 + 2          # setup, sytrd, tear/leaves, merges, unscale, ormtr
+    sytrd = 2 * (p - 144) + 1 if p > 144 else 1               # column + trailing-matrix launch per column, smem tail
+    ormtr = 3 + 2 * ((p - 1 + 127) // 128) if p >= 256 else 2   # blocked: gram, X, X*V, then 2 GEMMs per 128-block
+    eigh = 4 + sytrd + 4 + 5 * levels + 1 + ormtr              # setup, sytrd, zero/scale/tear/leaves, merges, unscale
     per_iter = 1 + eigh + 1 + 1 + 1                            # build_w, eigh, recon, prox+dual, stop
     return int(per_iter * len(sweeps))
 

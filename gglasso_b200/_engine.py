@@ -109,6 +109,21 @@ def to_host(t, chunk_bytes=32 << 20):
     return out
 
 
+_DEBUG_KEEP_INPUT = bool(int(os.environ.get("GG_DEBUG_KEEP_INPUT", "0")))
+_DEBUG_BUFFERS = []
+
+
+def _debug_check(st, it, where, **arrays):
+    """diagnostics (GG_DEBUG_KEEP_INPUT=1): first non-finite array of an iteration -> exception naming it"""
+    torch.cuda.current_stream().synchronize()
+    for name, a in arrays.items():
+        fin = torch.isfinite(a.reshape(a.shape[0], -1)).all(dim=1)
+        if not bool(fin.all()):
+            bad = torch.nonzero(~fin).flatten().tolist()
+            raise FloatingPointError(f"non-finite {name} {where}, iteration {it}, matrices {bad}, "
+                                     f"ctrl={st.ctrl[0, :9].tolist()}")
+
+
 class Eigh:
     """workspace + call wrapper for gg_eigh / gg_recon on (M,p,p) stacks."""
 
@@ -124,6 +139,15 @@ class Eigh:
         self.sweeps = []
 
     def eigh(self, A, ctrl=None, mpp=1, vectors=1, stream=0, warm=None):
+        if _DEBUG_KEEP_INPUT:
+            # diagnostics (GG_DEBUG_KEEP_INPUT=1): keep a host copy of the last input of every workspace so that a
+            # failing decomposition can be replayed (scripts/gpu_replay_eigh.py)
+            if not hasattr(self, "_dbg"):
+                self._dbg = torch.empty(A.shape, dtype=A.dtype, pin_memory=True)
+                _DEBUG_BUFFERS.append((self, self._dbg))
+            torch.cuda.current_stream().synchronize()
+            self._dbg.copy_(A)
+            self._dbg_args = (mpp, vectors, None if ctrl is None else ctrl.detach().cpu().numpy().copy())
         rc = self.lib.gg_eigh(_p(A), _p(self.D), self.M, self.p, _p(ctrl), mpp, _p(self.ws), self.ws_bytes,
                               vectors, self.nb2, 0.0, 0, self.quad_tol, self.info, _p(warm), stream)
         _lib.check(rc, "gg_eigh")
@@ -368,6 +392,8 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             torch.cuda.synchronize()
             t0 = time.time()
         st.omega_step()
+        if _DEBUG_KEEP_INPUT:
+            _debug_check(st, it, "after omega_step", D=st.eig.D, Vt=st.W, Omega_new=st.Omega_new)
         if measure and kind == "mgl":
             # log det Omega_k = sum_i log phi+(d_i, beta_k) from the eigenvalues of W that are resident right now
             # (no extra eigendecomposition); tiny (K,p) reduction, kept on the device until the objective is formed
@@ -387,6 +413,8 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             _lib.check(lib.gg_prox_sgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
                                        _p(st.ctrl), float(lambda1), _p(st.lam_mat), M, p, _p(partials), _p(st.pvec),
                                        stream), "gg_prox_sgl")
+        if _DEBUG_KEEP_INPUT:
+            _debug_check(st, it, "after prox", Theta=st.Theta, X=st.X)
         if latent:
             st.l_step()
             _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L),

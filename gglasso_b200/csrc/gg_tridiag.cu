@@ -22,6 +22,8 @@
 #include "gg_common.cuh"
 #include "gg_jacobi_dev.cuh"
 #include <stdlib.h>
+#include <cmath>
+#include <vector>
 
 #define TR_EPS 2.220446049250313e-16
 #define DC_LEAF 32
@@ -372,7 +374,10 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
     TR_STAMP(1, 6);
 }
 
-__global__ void __launch_bounds__(256, 4)
+// (256, 3): 80 registers, no spills.  (256, 4) -- 64 registers, 28 bytes of spills -- was 3 % faster on a single
+// stream but produced non-finite eigenvalues for single matrices when five host threads drove five solves
+// concurrently (bisected on the B200); not understood, so not used.
+__global__ void __launch_bounds__(256, 3)
 tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt)
 {
     __shared__ SvSmem sm;
@@ -670,7 +675,7 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
     int* rp = ws.rotp + (size_t)m * n + lo;
     int* rn = ws.rotn + (size_t)m * n + lo;
     __shared__ int s_k, s_ndf, s_nrot;
-    __shared__ double s_rho;
+    __shared__ double s_rho, s_red[64], s_max[2];
     const int tid = threadIdx.x, nt = blockDim.x;
     double* Qm = Qin + (size_t)m * n * n;
     double* Qo = Qout + (size_t)m * n * n;
@@ -695,9 +700,17 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
         idx[r] = i;
     }
     __syncthreads();
+    {
+        double dm = 0.0, zm = 0.0;
+        for (int i = tid; i < N; i += nt) { dm = fmax(dm, fabs(sd[i])); zm = fmax(zm, fabs(sz[i])); }
+        dm = gg_block_max(dm, s_red);
+        __syncthreads();
+        zm = gg_block_max(zm, s_red + 32);
+        if (tid == 0) { s_max[0] = dm; s_max[1] = zm; }
+    }
+    __syncthreads();
     if (tid == 0) {
-        double dmax = 0.0, zmax = 0.0;
-        for (int i = 0; i < N; ++i) { dmax = fmax(dmax, fabs(sd[i])); zmax = fmax(zmax, fabs(sz[i])); }
+        const double dmax = s_max[0], zmax = s_max[1];
         const double tol = 8.0 * TR_EPS * fmax(dmax, zmax);
         int k = 0, ndf = 0, nrot = 0, pj = -1;
         if (rho * zmax <= tol) {
@@ -708,11 +721,14 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
                 if (rho * fabs(sz[nj]) <= tol) { df[ndf++] = nj; continue; }
                 if (pj < 0) { pj = nj; continue; }
                 double s = sz[pj], c = sz[nj];
-                const double tau = sqrt(c * c + s * s);          // |z| <= 1 after normalisation: no overflow
-                const double itau = 1.0 / tau;
+                const double den = c * c + s * s;                // |z| <= 1 after normalisation: no overflow
                 const double tt = sd[nj] - sd[pj];
-                c *= itau; s = -s * itau;
-                if (fabs(tt * c * s) <= tol) {
+                // |t c s| <= tol with c = z_nj/tau, s = -z_pj/tau, tau^2 = den: tested without the square root and
+                // the division, which are only needed for the (rare) rotation -- this loop is one serial thread
+                if (fabs(tt * c * s) <= tol * den) {
+                    const double tau = sqrt(den);
+                    const double itau = 1.0 / tau;
+                    c *= itau; s = -s * itau;
                     sz[nj] = tau; sz[pj] = 0.0;
                     rp[nrot] = pj; rn[nrot] = nj; rc[nrot] = c; rs[nrot] = s; ++nrot;
                     const double tnew = sd[pj] * c * c + sd[nj] * s * s;
@@ -1469,6 +1485,18 @@ static int dc_levels(int n)
     return L;
 }
 
+// diagnostics (GG_DEBUG_STAGE=1): synchronise and test an (M,n) array for non-finite entries on the host
+static int dbg_nonfinite(const double* dptr, int M, int n, int ncheck, cudaStream_t s)
+{
+    std::vector<double> h((size_t)M * n);
+    if (cudaMemcpyAsync(h.data(), dptr, sizeof(double) * M * n, cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
+    for (int m = 0; m < M; ++m)
+        for (int i = 0; i < ncheck; ++i)
+            if (!std::isfinite(h[(size_t)m * n + i])) return 1;
+    return 0;
+}
+
 // write-back depth of the tridiagonalisation (see TR_QMAX): env GG_TR_LAZY in [1, TR_QMAX], default 3
 int gg_tr_lazy_depth()
 {
@@ -1572,7 +1600,9 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         cudaLaunchConfig_t cfg = {};
         cfg.stream = s;
         cfg.attrs = pdl;
-        cfg.numAttrs = 1;
+        static int no_pdl = -1;
+        if (no_pdl < 0) { const char* ev = getenv("GG_NO_PDL"); no_pdl = ev ? atoi(ev) : 0; }
+        cfg.numAttrs = no_pdl ? 0 : 1;
         const int js = (which == 1 || which == 2) ? n : (n > TR_TAIL ? n - TR_TAIL : 0);   // tail takes over at column js
         const int lazy_q = gg_tr_lazy_depth();
         int kb = 0;                                   // pairs kb..j-1 are pending at step j
@@ -1615,6 +1645,13 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         }
     }
     GG_CHECK_LAUNCH();
+    static int dbg_stage = -1;
+    if (dbg_stage < 0) { const char* ev = getenv("GG_DEBUG_STAGE"); dbg_stage = ev ? atoi(ev) : 0; }
+    if (dbg_stage && (which == 0 || which == 4)) {
+        if (dbg_nonfinite(tw.d, M, n, n, s)) return -11;
+        if (dbg_nonfinite(tw.e, M, n, n - 1, s)) return -12;
+        if (dbg_nonfinite(tw.tau, M, n, n - 1, s)) return -13;
+    }
     if (stop_after == 1 || (which != 0 && which != 4)) return 0;
 
     // ---- stage 3 preparation: G, X, V' of the blocked back-transformation (independent of stage 2).
@@ -1648,6 +1685,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     }
     dc_leaf_kernel<<<dim3(1 << L, M), 128, 0, s>>>(tw.d, tw.e, n, L, dw.lam[L & 1], qbuf[L & 1], skip);
     GG_CHECK_LAUNCH();
+    if (dbg_stage && dbg_nonfinite(dw.lam[L & 1], M, n, n, s)) return -14;
     {
         static bool attr = false;
         if (!attr) {
@@ -1670,6 +1708,9 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         dc_vectors_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, 0, s>>>(n, l, dw, skip);
         dc_gemm_kernel<<<dim3((Nmax + DG_T - 1) / DG_T, (Nmax + DG_T - 1) / DG_T, nodes * M), 256, 0, s>>>(n, l, Qin, Qout, dw, skip);
         GG_CHECK_LAUNCH();
+        if (dbg_stage) {
+            if (dbg_nonfinite(dw.lam[l & 1], M, n, n, s)) return -20 - l;
+        }
     }
     // eigenvalues of the root are in lam[0]; eigenvectors of T (rows) in A
     dc_unscale_kernel<<<dim3(4, M), 256, 0, s>>>(dw.lam[0], scale, n, D, skip);
