@@ -87,7 +87,7 @@ __device__ __forceinline__ double tr_block_allsum(double v, double* scratch)
 // v_j.  The step sits on the critical path of the launch chain, so every independent global load (row j, y,
 // v_{j-1}) is issued up front into registers: the dependent chain is one memory round trip, two block reductions
 // (one barrier each) and the stores.   Element i = j + tid + e*blockDim.x, e < EPT.
-template <int EPT, int THR>
+template <int EPT, int THR, bool PREF>
 __global__ void __launch_bounds__(THR)
 tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const int* __restrict__ skip)
 {
@@ -126,8 +126,22 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
     double tp = 0.0, yj = 0.0;
     if (j >= 1) { tp = tau[j - 1]; yj = y[j]; }
     // older pending pairs kb..j-2 (independent of w_{j-1}): a_i -= v_k[i] w_k[j] + w_k[i] v_k[j]
-    // (fully unrolled with predicates so that all of these loads are in flight together with the ones above)
-    {
+    // (PREF: fully unrolled with predicates so that all of these loads are in flight together with the ones above;
+    //  the large-p variant keeps them in a loop -- no register spills in any kernel of the launch chain)
+    if (!PREF) {
+        if (sk) return;
+        for (int q = 0; q < cnt - 1; ++q) {
+            const int k = kb + q;
+            const double* wk = wring + (size_t)(k % TR_QMAX) * n;
+            const double* vk = Vhm + (size_t)k * n;
+            const double wkj1 = wk[j], vkj1 = vk[j];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = j + tid + e * nt;
+                if (i < n) a[e] = a[e] - vk[i] * wkj1 - wk[i] * vkj1;
+            }
+        }
+    } else {
         double wkj[TR_QMAX - 1], vkj[TR_QMAX - 1], wki[TR_QMAX - 1][EPT], vki[TR_QMAX - 1][EPT];
 #pragma unroll
         for (int q = 0; q < TR_QMAX - 1; ++q) {
@@ -1609,13 +1623,13 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         for (int j = 0; j < js; ++j) {
             if (which != 2) {
                 const int len = n - j;
-                const int thr = len <= 2048 ? 256 : 1024;
+                const int thr = len <= 2048 ? 256 : 512;
                 cfg.gridDim = dim3(M); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = 0;
                 cudaError_t e;
-                if (len <= 512) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<2, 256>, (const double*)A, n, j, kb, tw, (const int*)skip);
-                else if (len <= 1024) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<4, 256>, (const double*)A, n, j, kb, tw, (const int*)skip);
-                else if (len <= 2048) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 256>, (const double*)A, n, j, kb, tw, (const int*)skip);
-                else if (len <= 8192) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 1024>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                if (len <= 512) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<2, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else if (len <= 1024) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<4, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else if (len <= 2048) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                else if (len <= 8192) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<16, 512, false>, (const double*)A, n, j, kb, tw, (const int*)skip);
                 else return -5;
                 if (e != cudaSuccess) return (int)e;
             }

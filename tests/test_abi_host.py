@@ -89,3 +89,23 @@ def test_signature_parity_with_reference_defaults():
     assert list(blk.parameters) == ["S", "lambda1", "Omega_0", "Theta_0", "X_0", "rho", "max_iter", "tol", "rtol",
                                     "stopping_criterion", "update_rho", "verbose", "measure", "lambda1_mask"]
     assert blk.parameters["rtol"].default == 1e-3 and blk.parameters["Theta_0"].default is None
+
+
+def test_launch_chain_kernels_do_not_spill():
+    """The kernels of the tridiagonalisation launch chain (programmatic dependent launch, work issued before
+    griddepcontrol.wait) must not have a stack frame: a 64-register build of tr_symv_kernel with 28 bytes of spills
+    live across the wait returned non-finite eigenvalues when several streams were active."""
+    import shutil
+    import subprocess
+    from gglasso_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library not available")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    lines = out.splitlines()
+    seen = 0
+    for i, line in enumerate(lines):
+        if "Function" in line and any(k in line for k in ("tr_symv_kernel", "tr_col_kernel", "tr_tail_kernel")):
+            usage = lines[i + 1]
+            assert "STACK:0 " in usage, (line.strip(), usage.strip())
+            seen += 1
+    assert seen >= 6          # symv, tail, four column-kernel instantiations
