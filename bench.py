@@ -1,26 +1,31 @@
 """bench.py -- headline benchmark of the B200 ADMM hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3|cfg4col]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-cpu] [--no-grid] [--no-weak]
 
-Metric (BASELINE.json): ADMM iterations/sec for the fused multiple graphical lasso K=20, p=1000
-(cfg3: ADMM_MGL, reg='FGL', lambda1=0.05, lambda2=0.01, N=2000 samples per instance, rho=1, update_rho).
+Metric (BASELINE.json): ADMM iterations/sec AND time-to-tolerance for the fused multiple graphical lasso K=20, p=1000
+(cfg3: ADMM_MGL, reg='FGL', lambda1=0.05, lambda2=0.01, N=2000 samples per instance, rho=1, update_rho=True), plus the
+10x10 lambda grid (cfg4) as a secondary block.  Inputs come from the REFERENCE's own seeded generators
+(time_varying_power_network(1000, 20, 10, seed=1234) + sample_covariance_matrix(N=2000, seed=1234), run from oracle/_ref
+through oracle/ref_inputs.py, cached under /tmp) -- input preparation only, outside every timed region.
 A "step" is one ADMM iteration over the whole (K,p,p) stack.
 
-  value : iterations/sec with S resident in HBM, timed with CUDA events around exactly --steps
-          iterations (each iteration reads/writes 160 MB arrays: working set >> 126 MB L2)
-  e2e   : same metric through the public reference-signature call ADMM_MGL(S_host, ...) with
-          max_iter = --steps: host->device copy of S/Omega_0, the iterations, post-loop checks and
-          the device->host copy of sol are all inside the timed region
-  roofline : dominant kernel of the step (tr_symv_kernel: trailing-matrix pass of the tridiagonalisation, HBM bound)
-  cpu_baseline : the oracle port (numpy/LAPACK + C prox; same algorithm as the reference) timed on
-          the host cores for a bounded number of iterations of the same workload
+  value        iterations/sec with S resident in HBM, CUDA events around exactly --steps iterations (stopping test
+               disabled by tol=rtol=0; every iteration streams >10 arrays of 160 MB: working set >> 126 MB L2)
+  e2e          the same through the public reference-signature call ADMM_MGL(S_host, ...) with max_iter=--steps:
+               H2D of S / Omega_0, the iterations, post-loop checks and the D2H of sol are inside the timed region
+  time_to_tol  wall seconds of the public call to tol=rtol=1e-7 (host buffers in, host buffers out), its iteration
+               count, and the final objective / sparsity pattern checked against the real reference's fixture
+  roofline     dominant kernel of the step, timed live with CUDA events on the launch stream
+  cpu_baseline the REAL reference (oracle/_ref: numpy/LAPACK + numba) on this host's cores: one full solve to
+               tol=rtol=1e-7 of the same input (11 iterations); value = its in-loop iterations/sec, plus its wall time
 
-N > 1 (torchrun, one rank per GPU): ONE fused-MGL problem with K = 20*N instances, 20 per rank (weak
-scaling).  Everything per instance stays local; the cross-instance TV prox needs all K values of an entry,
-so V = Omega + X is re-tiled instance-layout -> row-band layout with an NCCL all-to-all, the prox runs on the
-band and Theta travels back with a second all-to-all; 5 residual sums are all-reduced.  `value` counts units of
-(K=20, p=1000) stacks processed per second over all ranks = N * iterations/sec.
---impl reference : rank 0 times the CPU oracle port on the same config.
+N > 1 (torchrun, one rank per GPU) -- STRONG scaling of the same workload: ONE K=20, p=1000 problem, the instances
+sharded 10/10, 5x4 or 3,3,3,3,2,2,2,2 over the ranks.  Everything per instance stays local; the cross-instance TV prox
+needs all K values of an entry, so V = Omega + X is re-tiled instance layout -> row-band layout with an NCCL all-to-all,
+the prox runs on the band and Theta travels back with a second all-to-all; 5 residual sums are all-reduced.  `value` =
+iterations/sec of that one solve.  The sharded solve is checked inside the bench against the reference fixture
+(`dist_check`).  The previous weak-scaling run (K = 20*N) is kept as the extra key `weak`.
+--impl reference : rank 0 times the real reference (CPU) on the same config; other ranks exit.
 """
 import argparse
 import contextlib
@@ -37,11 +42,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(K=20, p=1000, N=2000, lambda1=0.05, lambda2=0.01, reg="FGL", seed=1234)
+WORKLOAD = ("cfg3: ADMM_MGL FGL K=20 p=1000 N=2000 lambda1=0.05 lambda2=0.01, inputs from the reference generators "
+            "time_varying_power_network(1000,20,10,seed=1234) + sample_covariance_matrix(N=2000,seed=1234)")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def make_input(cfg):
-    from gglasso_b200.datagen import synthetic_mgl
-    return synthetic_mgl(cfg["K"], cfg["p"], N=cfg["N"], seed=cfg["seed"], kind="fused")
+def load_input(name="cfg3"):
+    """reference-generated input (see module docstring); local rank 0 fills the cache, the others wait for the file"""
+    from oracle import ref_inputs
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    path = os.path.join(ref_inputs.CACHE, name + "_S.npy")
+    if local != 0:
+        t0 = time.time()
+        while not os.path.isfile(path) and time.time() - t0 < 600:
+            time.sleep(0.5)
+    return ref_inputs.load(name)
+
+
+def input_check(name, S):
+    from oracle import ref_inputs
+    try:
+        return ref_inputs.check_fingerprint(name, S, os.path.join(GOLDEN, "large_inputs.json"))
+    except Exception as ex:                                   # noqa: BLE001
+        return f"unavailable: {type(ex).__name__}"
 
 
 class ClockSampler:
@@ -88,55 +111,86 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_reference_rate(S, cfg, iters):
-    """oracle port (CPU): iterations/sec for `iters` iterations of the same workload, all host threads
-    (torchrun exports OMP_NUM_THREADS=1; the BLAS pool is widened explicitly)."""
-    from oracle import admm_oracle as orc
-    orc.build_c()
-    try:
+# ------------------------------------------------------------------------------------------------------------------
+# CPU: the real reference (oracle/_ref), timed on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def _widen_threads():
+    try:                                   # torchrun exports OMP_NUM_THREADS=1; the BLAS pool is widened explicitly
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=os.cpu_count())
     except Exception:
         pass
+
+
+def reference_solver():
+    """(callable, kind): the real reference's ADMM_MGL from oracle/_ref, else the oracle port"""
+    from oracle import ref
+    if ref.available():
+        ADMM_MGL_ref, _, _ = ref.fresh_solvers()
+        return ADMM_MGL_ref, "reference"
+    from oracle import admm_oracle as orc
+    orc.build_c()
+
+    def port(S, l1, l2, reg, Om0, tol=1e-7, rtol=1e-7, max_iter=1000, measure=False, **kw):
+        t0 = time.perf_counter()
+        sol, info = orc.admm_mgl(S, l1, l2, reg, Om0, tol=tol, rtol=rtol, max_iter=max_iter)
+        n = info["iterations"]
+        return sol, {"status": info["status"], "runtime": np.full(n, (time.perf_counter() - t0) / n)}
+    return port, "port"
+
+
+def cpu_reference(S, cfg, max_iter, tol):
+    """one call of the reference solver: (in-loop iterations/sec, iterations, wall seconds, kind)"""
+    _widen_threads()
+    solver, kind = reference_solver()
     K, p = cfg["K"], cfg["p"]
     Om0 = np.repeat(np.eye(p)[None], K, 0)
     small = np.repeat(np.eye(8)[None], 2, 0)
-    orc.admm_mgl(small, 0.1, 0.1, cfg["reg"], small, max_iter=2)           # warm-up
-    t0 = time.perf_counter()
-    _, info = orc.admm_mgl(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=1e-7, rtol=1e-7, max_iter=iters)
-    dt = time.perf_counter() - t0
-    return info["iterations"] / dt, info["iterations"], dt
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver(small + 0.1, 0.1, 0.1, cfg["reg"], small, max_iter=2, measure=True)          # numba compilation
+        t0 = time.perf_counter()
+        _, info = solver(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=tol, rtol=tol, max_iter=max_iter,
+                         measure=True)
+        wall = time.perf_counter() - t0
+    rt = np.asarray(info["runtime"], dtype=float)
+    return rt, wall, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    S = make_input(CFG)
-    steps = max(1, min(args.steps, 4))
-    if args.warmup > 0:
-        cpu_reference_rate(S, CFG, 1)
-    rate, n, dt = cpu_reference_rate(S, CFG, steps)
+    S = load_input("cfg3")
+    # the reference needs ~2-4 s per iteration here: bound the sample so that the arm ends within a few minutes
+    warm = min(args.warmup, 3)
+    steps = max(1, min(args.steps, 12))
+    rt, wall, kind = cpu_reference(S, CFG, warm + steps, 0.0)
+    used = rt[warm:warm + steps]
+    rate = len(used) / float(used.sum())
     cores = os.cpu_count()
     line = {"impl": "reference", "metric": "admm_iters_per_sec", "value": rate, "unit": "iter/s",
-            "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / rate,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg3: ADMM_MGL FGL K=20 p=1000 N=2000 lambda1=0.05 lambda2=0.01", **CFG},
-            "cpu_baseline": {"value": rate, "unit": "iter/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} ADMM iterations of the full K=20 p=1000 workload ({dt:.1f} s)"},
+            "n_gpus": args.gpus, "steps": int(len(used)), "warmup": warm, "ms_per_step": 1e3 / rate,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, **CFG},
+            "cpu_baseline": {"value": rate, "unit": "iter/s", "cores": cores, "kind": kind,
+                             "sample": f"{len(used)} ADMM iterations (after {warm} warm-up iterations) of the full K=20 "
+                                       f"p=1000 workload, in-loop time of the reference's own measure=True clock; "
+                                       f"requested steps/warmup {args.steps}/{args.warmup} bounded to keep the arm "
+                                       f"within minutes ({wall:.1f} s wall)"},
             "e2e": {"value": rate, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-iters", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-grid", action="store_true", help="skip the secondary cfg4 lambda-grid measurement")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling run (K = 20*N)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -144,7 +198,8 @@ def main():
     import torch
     import torch.distributed as dist
     from gglasso_b200 import ADMM_MGL, _lib
-    from gglasso_b200._engine import run_admm
+    import gglasso_b200._engine as eng
+    from gglasso_b200.parallel import ADMM_MGL_dist, run_admm_mgl_dist, partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -152,14 +207,15 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.load()
-    import gglasso_b200._engine as _eng
-    _eng.warmup()                              # one-time process init (pinned staging buffers), outside timed regions
+    lib = _lib.load()
+    eng.warmup()                              # one-time process init (pinned staging buffers), outside timed regions
     cfg = dict(CFG)
-    cfg["seed"] = CFG["seed"] + rank          # each rank: its own replica of the workload
-    S = make_input(cfg)
+    S_full = load_input("cfg3")
+    in_dev = input_check("cfg3", S_full) if rank == 0 else None
     K, p = cfg["K"], cfg["p"]
-    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    k_lo, k_hi = partition(K, world)[rank]
+    S = np.ascontiguousarray(S_full[k_lo:k_hi])
+    Om0 = np.repeat(np.eye(p)[None], k_hi - k_lo, 0)
     steps, warm = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -167,100 +223,139 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing: exactly `steps` iterations -------------------------
-    # run_admm is the engine behind ADMM_MGL; tol=0 disables the stopping test so that exactly
-    # warm+steps iterations execute; inputs are uploaded before the timed region.
-    import gglasso_b200._engine as eng
-    marks = {}
-    orig_step = eng.AdmmState.omega_step
-    count = {"n": 0}
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def stepped(self):
-        if count["n"] == warm:
+    def timed_loop(S_loc, Om_loc, K_total):
+        """exactly `steps` device-resident iterations (after `warm`), CUDA events on the launch stream, max over ranks"""
+        marks, count = {}, {"n": 0}
+        orig_step = eng.AdmmState.omega_step
+
+        def stepped(self):
+            if count["n"] == warm:
+                barrier()
+                marks["e0"] = torch.cuda.Event(enable_timing=True)
+                marks["e0"].record()
+            count["n"] += 1
+            return orig_step(self)
+
+        eng.AdmmState.omega_step = stepped
+        l0 = lib.gg_launch_count()
+        try:
+            if world == 1:
+                st, _ = eng.run_admm("mgl", S_loc, Om_loc, None, None, lambda1=cfg["lambda1"], lambda2=cfg["lambda2"],
+                                     reg=cfg["reg"], tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
+            else:
+                st, _ = run_admm_mgl_dist(S_loc, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om_loc, K_total=K_total,
+                                          tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
             barrier()
-            marks["e0"] = torch.cuda.Event(enable_timing=True)
-            marks["e0"].record()
-        count["n"] += 1
-        return orig_step(self)
+        finally:
+            eng.AdmmState.omega_step = orig_step
+        launches = (lib.gg_launch_count() - l0) * steps // (warm + steps)
+        return st, max_over_ranks(marks["e0"].elapsed_time(e1)), int(launches)
 
-    eng.AdmmState.omega_step = stepped
-    from gglasso_b200.parallel import ADMM_MGL_dist, run_admm_mgl_dist
+    # ---------------- device-resident timing -----------------------------------------------------------------------
     with ClockSampler(local) as clk:
-        if world == 1:
-            st, res = run_admm("mgl", S, Om0, None, None, lambda1=cfg["lambda1"], lambda2=cfg["lambda2"],
-                               reg=cfg["reg"], tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
-        else:
-            # one MGL problem with K = 20*N instances, 20 per rank: per-instance work stays local, the
-            # cross-instance prox goes through two all-to-all re-tiles per iteration (weak scaling)
-            st, _ = run_admm_mgl_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K * world,
-                                      tol=0.0, rtol=0.0, max_iter=warm + steps, check_every=10 ** 9)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
-        barrier()
-    eng.AdmmState.omega_step = orig_step
-    ms = marks["e0"].elapsed_time(e1)
-    sweeps = [0] * steps
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * steps / (ms / 1e3)
+        st, ms, launches = timed_loop(S, Om0, K)
+    value = steps / (ms / 1e3)
 
-    # ---------------- kernel-level roofline of the dominant kernel -------------------------------
-    roof = kernel_roofline(st, sweeps, ms / steps) if rank == 0 else None
+    # ---------------- kernel-level roofline of the dominant kernel (rank 0) ----------------------------------------
+    roof = kernel_roofline(st, ms / steps) if rank == 0 else None
+    del st
 
-    # ---------------- end to end through the public API (host buffers) ---------------------------
+    # ---------------- end to end through the public API (host buffers), `steps` iterations -------------------------
+    def public_call(max_iter, tol):
+        with contextlib.redirect_stdout(io.StringIO()):
+            if world == 1:
+                return ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=tol, rtol=tol,
+                                max_iter=max_iter)
+            sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K, tol=tol, rtol=tol,
+                                      max_iter=max_iter, check_every=10 ** 9 if tol == 0.0 else 1)
+            return sol, info
+
     dt = None
     for rep in range(2):          # first call = warm-up (lazy kernel module loading, allocator); second is reported
         barrier()
         t0 = time.perf_counter()
-        with contextlib.redirect_stdout(io.StringIO()):
-            if world == 1:
-                sol, info = ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=0.0, rtol=0.0,
-                                     max_iter=steps)
-            else:
-                sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K * world,
-                                          tol=0.0, rtol=0.0, max_iter=steps, check_every=10 ** 9)
-                sol.pop("L")
+        sol, info = public_call(steps, 0.0)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    e2e = steps / max_over_ranks(dt)
+    h2d = (S_full.nbytes + S_full.nbytes) / steps                       # S and Omega_0 of all ranks
+    d2h = 3 * S_full.nbytes / steps                                     # Omega, Theta, X of all ranks
+
+    # ---------------- time to tolerance through the public API + parity against the reference fixture --------------
+    barrier()
+    t0 = time.perf_counter()
+    sol, info = public_call(1000, 1e-7)
+    torch.cuda.synchronize()
+    ttt = max_over_ranks(time.perf_counter() - t0)
+    ttt_info = {"seconds": ttt, "tol": 1e-7, "status": info["status"],
+                "iterations": int(info["iterations"]) if "iterations" in info else None,
+                "what": "public call, host buffers in and out, H2D + loop + post-checks + D2H"}
+    check = fixture_check(sol["Theta"], k_lo, k_hi, p, world)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = world * steps / float(t.item())
-    h2d = world * (S.nbytes + Om0.nbytes) / steps
-    d2h = world * sum(v.nbytes for k, v in sol.items() if not (k == "L")) / steps
+        gathered = [None] * world
+        dist.all_gather_object(gathered, check)
+        check = {"pattern_identical": all(g["pattern_identical"] for g in gathered),
+                 "theta_rel_err": float(np.sqrt(sum(g["err2"] for g in gathered) / sum(g["ref2"] for g in gathered))),
+                 "fixture": gathered[0]["fixture"]}
+    else:
+        check = {"pattern_identical": check["pattern_identical"],
+                 "theta_rel_err": float(np.sqrt(check["err2"] / check["ref2"])), "fixture": check["fixture"]}
+    assert check["pattern_identical"] and check["theta_rel_err"] < 1e-8, check
+    del sol
+
+    # ---------------- extra: weak scaling (K = 20 per rank), as measured in round 1 --------------------------------
+    weak = None
+    if world > 1 and not args.no_weak:
+        Omf = np.repeat(np.eye(p)[None], K, 0)
+        _, wms, _ = timed_loop(S_full, Omf, K * world)
+        weak = {"K_total": K * world, "ms_per_step": wms / steps, "units_per_s": world * steps / (wms / 1e3),
+                "what": "ONE fused-MGL problem with K = 20 per rank (20*N instances), device resident"}
 
     line = None
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
-            rate, n, cdt = cpu_reference_rate(make_input(CFG), CFG, args.cpu_iters)
-            cpu = {"value": rate, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"{n} ADMM iterations of the full K=20 p=1000 workload ({cdt:.1f} s)"}
-        launches = launches_per_iter(p, K, sweeps)
+            rt, wall, kind = cpu_reference(S_full, CFG, 1000, 1e-7)
+            cpu = {"value": len(rt) / float(rt.sum()), "unit": "iter/s", "cores": os.cpu_count(), "kind": kind,
+                   "time_to_tol_s": wall, "iterations_to_tol": int(len(rt)),
+                   "sample": f"one full solve to tol=rtol=1e-7 of the same input: {len(rt)} iterations, in-loop "
+                             f"{rt.sum():.1f} s (reference's measure=True clock), {wall:.1f} s wall incl. objective and checks"}
+            ttt_info["cpu_seconds"] = wall
+        shard = "single GPU" if world == 1 else (
+            f"strong scaling: the K=20 instances sharded {[hi - lo for lo, hi in partition(K, world)]} over {world} "
+            "GPUs; cross-instance prox via 2 NCCL all-to-all re-tiles per iteration, 5-double all-reduce")
         line = {"metric": "admm_iters_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": steps,
-                "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cfg3: ADMM_MGL FGL K=20 p=1000 N=2000 lambda1=0.05 lambda2=0.01", **CFG,
+                "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, **CFG,
                            "l2": "inputs larger than L2 (each (K,p,p) FP64 array is 160 MB; >10 arrays per step)",
-                           "K_total": K * world, "partition": "K-sharded (20 instances per GPU); cross-instance prox via 2 all-to-all re-tiles per iteration" if world > 1 else "single GPU",
-                           "eigh": "sytrd + divide&conquer + ormtr (hand-written)"},
+                           "K_total": K, "partition": shard, "input_fingerprint_dev": in_dev,
+                           "eigh": "blocked sytrd (cluster panel kernel + DMMA syr2k) + divide&conquer + ormtr, hand-written"},
                 "e2e": {"value": e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "grid": None}
+                "time_to_tol": ttt_info, "parity": check,
+                "gpu_launches": launches * world, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "weak": weak, "grid": None}
 
     # secondary measurement, last: the headline line above is complete before it starts and is printed even if the
     # grid run fails (single process; with several ranks a failure surfaces through torchrun)
     if not args.no_grid:
         if world == 1:
             try:
-                line["grid"] = grid_bench(world, rank, barrier)
+                line["grid"] = grid_bench(world, rank, barrier, max_over_ranks)
             except Exception as ex:                                   # noqa: BLE001
                 line["grid"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
                 print(json.dumps(line), flush=True)
                 os._exit(0)
         else:
-            g = grid_bench(world, rank, barrier)
+            g = grid_bench(world, rank, barrier, max_over_ranks)
             if rank == 0:
                 line["grid"] = g
     if rank == 0:
@@ -269,15 +364,27 @@ def main():
         dist.destroy_process_group()
 
 
-def grid_bench(world, rank, barrier):
+def fixture_check(Theta, k_lo, k_hi, p, world):
+    """final Theta of the solve to tol=1e-7 against the real reference's result (tests/golden/cfg3_fgl_full.npz)"""
+    g = np.load(os.path.join(GOLDEN, "cfg3_fgl_full.npz"))
+    idx, val = g["theta_idx"], g["theta_val"]
+    lo, hi = k_lo * p * p, k_hi * p * p
+    m = (idx >= lo) & (idx < hi)
+    ref = np.zeros((k_hi - k_lo) * p * p)
+    ref[idx[m] - lo] = val[m]
+    mine = Theta.reshape(-1)
+    return {"pattern_identical": bool(np.array_equal(mine != 0, ref != 0)),
+            "err2": float(np.sum((mine - ref) ** 2)), "ref2": float(np.sum(ref ** 2)),
+            "fixture": "tests/golden/cfg3_fgl_full.npz (real reference, 11 iterations, objective 11752.409197493562)"}
+
+
+def grid_bench(world, rank, barrier, max_over_ranks):
     """secondary measurement named by BASELINE.json's metric: the 10x10 lambda1 x lambda2 model-selection grid
-    (cfg4: GGL, K=10, p=500, N=1000, eBIC gamma=0.1, tol=rtol=1e-7), device resident (scores and warm starts stay on
-    the GPU), lambda1 columns sharded over the ranks and 5 columns concurrently per GPU; time = max over ranks."""
-    import torch
-    import torch.distributed as dist
-    from gglasso_b200.datagen import synthetic_mgl
+    (cfg4: GGL, K=10, p=500, N=1000, eBIC gamma=0.1, tol=rtol=1e-7; input from group_power_network(500,10,10,seed=1234)),
+    device resident (scores and warm starts stay on the GPU), lambda1 columns sharded over the ranks and 5 columns
+    concurrently per GPU; time = max over ranks.  The eBIC table is compared with the real reference's."""
     from gglasso_b200.parallel import grid_search_device
-    Sg = synthetic_mgl(10, 500, N=1000, seed=1234)
+    Sg = load_input("cfg4")
     Ng = np.full(10, 1000)
     l1, l2 = np.logspace(0, -3, 10), np.logspace(-1, -4, 10)
     grid_search_device(Sg, Ng, "GGL", l1[4:5], l2[:2], gamma=0.1, tol=1e-5, rtol=1e-5)        # warm-up
@@ -285,34 +392,25 @@ def grid_bench(world, rank, barrier):
     t0 = time.perf_counter()
     scores, iters, ix, best = grid_search_device(Sg, Ng, "GGL", l1, l2, gamma=0.1, tol=1e-7, rtol=1e-7, n_streams=5)
     barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"workload": "cfg4: 10x10 lambda grid, GGL K=10 p=500 N=1000, eBIC(0.1), tol=rtol=1e-7", "seconds": float(t.item()),
-            "admm_iterations": int(iters.sum()), "grid_points": int(scores.size), "streams_per_gpu": 5,
-            "best_lambda": [float(l1[ix[1]]), float(l2[ix[0]])], "scaling": "strong (columns sharded over ranks)"}
+    dt = max_over_ranks(time.perf_counter() - t0)
+    out = {"workload": "cfg4: 10x10 lambda grid, GGL K=10 p=500 N=1000, eBIC(0.1), tol=rtol=1e-7, reference-generated input",
+           "seconds": dt, "admm_iterations": int(iters.sum()), "grid_points": int(scores.size), "streams_per_gpu": 5,
+           "best_lambda": [float(l1[ix[1]]), float(l2[ix[0]])], "scaling": "strong (columns sharded over ranks)",
+           "start_points": "every lambda1 column starts from the identity (the reference chains columns too)"}
+    gpath = os.path.join(GOLDEN, "cfg4_grid.npz")
+    if os.path.isfile(gpath):
+        g = np.load(gpath)
+        if "bic_10x10" in g.files:
+            out["vs_reference_grid"] = {
+                "same_best_index": bool(tuple(int(i) for i in ix) == tuple(int(i) for i in g["ix_10x10"])),
+                "max_rel_dev_ebic": float(np.nanmax(np.abs(scores - g["bic_10x10"]) / np.abs(g["bic_10x10"]))),
+                "reference_wall_s": float(g["wall_10x10"]), "reference_cores": int(g["ref_cores"])}
+    return out
 
 
-def launches_per_iter(p, K, sweeps):
-    """kernel launches inside the timed region (all are kernels of libgglasso_b200.so)."""
-    levels = 0
-    while ((p + (1 << levels) - 1) >> levels) > 32:
-        levels += 1
-    sytrd = 2 * (p - 144) + 1 if p > 144 else 1               # column + trailing-matrix launch per column, smem tail
-    ormtr = 3 + 2 * ((p - 1 + 127) // 128) if p >= 256 else 2   # blocked: gram, X, X*V, then 2 GEMMs per 128-block
-    eigh = 4 + sytrd + 4 + 5 * levels + 1 + ormtr              # setup, sytrd, zero/scale/tear/leaves, merges, unscale
-    per_iter = 1 + eigh + 1 + 1 + 1                            # build_w, eigh, recon, prox+dual, stop
-    return int(per_iter * len(sweeps))
-
-
-def kernel_roofline(st, sweeps, ms_per_step):
-    """Dominant kernel of the step: tr_symv_kernel (trailing-matrix pass of the Householder
-    tridiagonalisation: applies the pending rank-2 update to the upper triangle and accumulates the full
-    symmetric A*v from that one half-matrix sweep; HBM/L2 bound).
-    Timed live with CUDA events on the launch stream through gg_sytrd_profile(which=2), which issues
-    exactly the (p-1) symv launches of one eigendecomposition of the batch."""
-    import ctypes
+def kernel_roofline(st, ms_per_step):
+    """Dominant kernel of the step, timed live with CUDA events on the launch stream through gg_sytrd_profile, which
+    issues exactly the launches of the selected kernel class of one tridiagonalisation of the batch."""
     import torch
     from gglasso_b200 import _lib
     from gglasso_b200._engine import _p
@@ -361,9 +459,7 @@ def kernel_roofline(st, sweeps, ms_per_step):
             "avg_ms_per_launch": times[2] / n_launch,
             "algorithmic_bytes_per_launch_avg": total_bytes / n_launch,
             "symv_ms_per_step": times[2], "col_kernels_ms_per_step": times[1], "sytrd_ms_per_step": times[0],
-            "share_of_step": times[2] / ms_per_step,
-            "note": "trailing blocks shrink from 160 MB to 0 over the launches; blocks below ~126 MB total are L2 resident, "
-                    "so late launches can exceed the HBM figure"}
+            "share_of_step": times[2] / ms_per_step}
 
 
 if __name__ == "__main__":

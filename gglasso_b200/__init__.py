@@ -23,6 +23,7 @@ def install():
     """
     import importlib
     patched = []
+    uninstall()
     targets = {
         "gglasso.solver.admm_solver": {"ADMM_MGL": ADMM_MGL},
         "gglasso.solver.single_admm_solver": {"ADMM_SGL": ADMM_SGL, "block_SGL": block_SGL},
@@ -40,6 +41,17 @@ def install():
             continue
         for n, fn in names.items():
             if hasattr(mod, n):
+                _ORIGINALS.append((mod, n, getattr(mod, n)))
                 setattr(mod, n, fn)
                 patched.append(f"{modname}.{n}")
     return patched
+
+
+_ORIGINALS = []
+
+
+def uninstall():
+    """undo ``install()``: restore the reference's own solver callables (used by tests that run both paths)."""
+    while _ORIGINALS:
+        mod, n, fn = _ORIGINALS.pop()
+        setattr(mod, n, fn)

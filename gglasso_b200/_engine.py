@@ -21,6 +21,10 @@ from . import _lib
 from ._lib import CTRL_STRIDE, HIST_STRIDE, NPART, C_DONE, C_ITER, C_RHO
 
 
+# largest K of the fused tile-pair MGL prox (K x 272 doubles of shared memory per CTA <= 200 KB)
+K_TILE_MAX = 90
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -362,7 +366,14 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     else:
         nparts_fused = lib.gg_sgl_nparts(p, M)
     nparts_dual = lib.gg_sgl_nparts(p, M) * mpp
-    nparts = nparts_dual if latent else nparts_fused
+    # K beyond the shared-memory layout of the fused tile-pair prox (K x 272 doubles per CTA): the row-band prox of the
+    # K-sharded path takes over on one device (pack -> band prox -> unpack fused with the dual update)
+    big_K = kind == "mgl" and M > K_TILE_MAX
+    nparts = nparts_dual if (latent or big_K) else nparts_fused
+    vband = tband = None
+    if big_K:
+        vband = torch.empty(M * p * p, dtype=torch.float64, device=st.dev)
+        tband = torch.zeros(M * p * p, dtype=torch.float64, device=st.dev)
     partials = torch.zeros((nprob, max(nparts_fused, nparts_dual), NPART), dtype=torch.float64, device=st.dev)
 
     blk_nrm = None
@@ -401,7 +412,14 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             Dw = st.eig.D
             logdet_dev = torch.log(0.5 * (torch.sqrt(Dw * Dw + 4 * beta[:, None]) + Dw)).sum()
         C = st.W if latent else None
-        if kind == "mgl":
+        if big_K:
+            _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), M, p, 1, _p(vband), stream),
+                       "gg_pack_bands")
+            _lib.check(lib.gg_prox_band(_p(vband), _p(tband), _p(st.ctrl), lambda1, lambda2, regi, M, p, p, 0, stream),
+                       "gg_prox_band")
+            _lib.check(lib.gg_unpack_dual(_p(tband), _p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta), _p(C),
+                                          _p(st.ctrl), M, p, 1, _p(partials), stream), "gg_unpack_dual")
+        elif kind == "mgl":
             _lib.check(lib.gg_prox_mgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
                                        _p(st.ctrl), lambda1, lambda2, regi, M, p, _p(partials), stream),
                        "gg_prox_mgl")
@@ -431,7 +449,11 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
                                           tol, rtol, 1 if update_rho else 0, nprob, stream), "gg_stop_update")
             st.swap()
             if trace is not None:       # test hook: per-iteration state (X before the rho rescale, like the oracle)
-                if st.ctrl[0, C_DONE].item() == 0 or st.ctrl[0, C_ITER].item() == it + 1:
+                if st.ctrl[0, C_DONE].item() != 0 and st.ctrl[0, C_ITER].item() != it + 1:
+                    pass
+                elif callable(trace):
+                    trace(st, it)
+                else:
                     trace.append(dict(Omega=st.Omega.cpu().numpy(), Theta=st.Theta.cpu().numpy(),
                                       L=None if st.L is None else st.L.cpu().numpy(), X=st.X.cpu().numpy()))
             if (it + 1) % check_every == 0 or it + 1 == max_iter:
@@ -521,7 +543,11 @@ def _kkt_residual(kind, st, lambda1, lambda2, regi, latent):
     zero = torch.zeros_like(Theta)
     P = torch.empty_like(Theta)
     Cdummy = torch.empty_like(Theta)
-    if kind == "mgl":
+    if kind == "mgl" and M > K_TILE_MAX:
+        _lib.check(lib.gg_add3(_p(Theta), _p(Xu), _p(zero), _p(Cdummy), M * p * p, stream), "gg_add3")
+        _lib.check(lib.gg_prox_band(_p(Cdummy), _p(P), _p(ctrl1), lambda1, lambda2, regi, M, p, p, 0, stream),
+                   "gg_prox_band")
+    elif kind == "mgl":
         _lib.check(lib.gg_prox_mgl(_p(Theta), _p(Theta), _p(Xu), _p(zero), _p(P), _p(Cdummy), _p(ctrl1), lambda1,
                                    lambda2, regi, M, p, None, stream), "gg_prox_mgl")
     else:

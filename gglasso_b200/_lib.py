@@ -21,6 +21,7 @@ _vp, _i, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size
 # name -> (restype, argtypes); mirrors include/gglasso_b200.h one to one
 SIGNATURES = {
     "gg_version": (_i, []),
+    "gg_launch_count": (ctypes.c_longlong, []),
     "gg_build_w": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gg_eigh_workspace_bytes": (_sz, [_i, _i]),
     "gg_eigh": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _sz, _i, _i, _d, _i, _d, ctypes.POINTER(_i), _vp, _vp]),
@@ -33,6 +34,8 @@ SIGNATURES = {
     "gg_mgl_ntile": (_i, [_i]),
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "gg_pack_bands": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "gg_unpack_dual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gg_prox_band": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, _i, _i, _i, _vp]),
     "gg_ext_theta": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "gg_ext_lambda": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),

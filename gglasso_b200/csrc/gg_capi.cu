@@ -32,11 +32,20 @@ int gg_launch_ext_lambda(const double*, const double*, const int*, int, int, int
 int gg_launch_ext_dual(double*, double*, const double*, const double*, const double*, const double*, const double*,
                        const double*, const double*, const int*, int, int, double*, cudaStream_t);
 int gg_launch_prox_band(const double*, double*, const double*, double, double, int, int, int, int, int, cudaStream_t);
+int gg_launch_pack_bands(const double*, const double*, const double*, const double*, int, int, int, double*, cudaStream_t);
+int gg_launch_unpack_dual(const double*, const double*, const double*, double*, double*, double*, const double*, int, int,
+                          int, double*, cudaStream_t);
 size_t gg_tridiag_ws_bytes(int, int);
 int gg_tr_lazy_depth();
 int gg_gershgorin_min_impl(const double*, int, int, void*, size_t, double*, cudaStream_t);
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void gg_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 extern "C" {
+
+long long gg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_bytes, int which, void* stream)
 {
@@ -147,6 +156,21 @@ int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lamb
 {
     if (K <= 0 || nb < 0 || p <= 0 || reg < 0 || reg > 1) return -1;
     return gg_launch_prox_band(V, Theta, ctrl, lambda1, lambda2, reg, K, nb, p, row0, (cudaStream_t)stream);
+}
+
+int gg_pack_bands(const double* Omega, const double* L, const double* X, const double* ctrl, int K_loc, int p, int world,
+                  double* send, void* stream)
+{
+    if (K_loc <= 0 || p <= 0 || world <= 0 || world > p) return -1;
+    return gg_launch_pack_bands(Omega, L, X, ctrl, K_loc, p, world, send, (cudaStream_t)stream);
+}
+
+int gg_unpack_dual(const double* recv, const double* Omega, const double* Omega_prev, double* X, double* Theta,
+                   double* C, const double* ctrl, int K_loc, int p, int world, double* partials, void* stream)
+{
+    if (K_loc <= 0 || p <= 0 || world <= 0 || world > p || ctrl == nullptr) return -1;
+    return gg_launch_unpack_dual(recv, Omega, Omega_prev, X, Theta, C, ctrl, K_loc, p, world, partials,
+                                 (cudaStream_t)stream);
 }
 
 int gg_ext_theta(const double* Omega, const double* L, const double* X0, const double* Lam, const double* X1,

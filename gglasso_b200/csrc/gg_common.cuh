@@ -22,6 +22,9 @@
 #define GG_HIST_STRIDE 5  // r, s, e_pri, e_dual, rho (value used during the iteration)
 #define GG_NPART 5        // |Omega|^2, |Theta-L|^2, |X|^2, |Omega-Theta+L|^2, |Omega-Omega_prev|^2
 
+// kernel-launch counter of the library (gg_launch_count() in the C ABI): every launch site calls it once per launch
+void gg_count_launch(int n);
+
 #define GG_CHECK_LAUNCH()                                   \
     do {                                                    \
         cudaError_t e__ = cudaGetLastError();               \

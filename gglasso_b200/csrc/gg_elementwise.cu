@@ -461,6 +461,73 @@ add3_kernel(const double* __restrict__ Omega, const double* __restrict__ L, cons
     }
 }
 
+// Row-band bookkeeping of the K-sharded solve: the p rows are cut into `world` contiguous bands (the first p % world
+// bands one row longer -- parallel.partition()); band d of this rank's K_loc instances is one contiguous block
+// [K_loc][rows_d][p] of the all-to-all buffers, at offset K_loc * p * lo_d.
+__device__ __forceinline__ size_t gg_band_offset(int m, int r, int c, int p, int K_loc, int world)
+{
+    const int base = p / world, rem = p - base * world, cut = rem * (base + 1);
+    const int d = r < cut ? r / (base + 1) : rem + (r - cut) / base;
+    const int lo = d < rem ? d * (base + 1) : cut + (d - rem) * base;
+    const int rows = base + (d < rem ? 1 : 0);
+    return (size_t)K_loc * p * lo + ((size_t)m * rows + (r - lo)) * p + c;
+}
+
+// send = (Omega + L) + X written straight into the send buffer of the first all-to-all (one pass, no torch.cat)
+__global__ void __launch_bounds__(EW_THREADS)
+pack_bands_kernel(const double* __restrict__ Omega, const double* __restrict__ L, const double* __restrict__ X,
+                  const double* __restrict__ ctrl, int p, int K_loc, int world, double* __restrict__ send)
+{
+    if (ctrl && ctrl[GG_C_DONE] != 0.0) return;
+    const int m = blockIdx.y;
+    const size_t pp = (size_t)p * p, base = (size_t)m * pp;
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int r = (int)(e / p), c = (int)(e - (size_t)r * p);
+        double v = Omega[base + e];
+        if (L) v = v + L[base + e];
+        send[gg_band_offset(m, r, c, p, K_loc, world)] = v + X[base + e];
+    }
+}
+
+// Theta arrives in the receive buffer of the second all-to-all (same block layout as the send buffer above): one
+// pass writes Theta in instance layout and either C = Theta - X - Omega (latent) or the dual update
+// X += Omega - Theta with the five residual partial sums (same expressions as prox_mgl_kernel's phase B).
+__global__ void __launch_bounds__(EW_THREADS)
+unpack_dual_kernel(const double* __restrict__ recv, const double* __restrict__ Omega,
+                   const double* __restrict__ Omega_prev, double* __restrict__ X, double* __restrict__ Theta,
+                   double* __restrict__ C, const double* __restrict__ ctrl, int p, int K_loc, int world,
+                   double* __restrict__ partials)
+{
+    __shared__ double scratch[GG_NPART * 32];
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const int m = blockIdx.y;
+    const size_t pp = (size_t)p * p, base = (size_t)m * pp;
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int r = (int)(e / p), c = (int)(e - (size_t)r * p);
+        const double th = recv[gg_band_offset(m, r, c, p, K_loc, world)];
+        const double om = Omega[base + e], x = X[base + e];
+        Theta[base + e] = th;
+        if (C) {
+            C[base + e] = (th - x) - om;
+        } else {
+            const double d1 = om - th;
+            const double xn = x + d1;
+            X[base + e] = xn;
+            const double d2 = om - Omega_prev[base + e];
+            acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
+        }
+    }
+    if (!C) {
+        gg_block_sum<GG_NPART>(acc, scratch);
+        if (threadIdx.x == 0) {
+            double* out = partials + ((size_t)m * gridDim.x + blockIdx.x) * GG_NPART;
+#pragma unroll
+            for (int q = 0; q < GG_NPART; ++q) out[q] = acc[q];
+        }
+    }
+}
+
 // V, Theta: (K, nb, p) slabs holding global rows row0..row0+nb-1 of every instance.  One thread per entry;
 // the K-vector lives in shared memory ([k][tid]: conflict free).  Every entry is computed from its own
 // inputs, so with symmetric inputs the assembled Theta is symmetric and identical to prox_mgl_kernel's.
@@ -638,6 +705,7 @@ int gg_launch_build_w(const double* Theta, const double* L, double* X, const dou
 {
     const size_t pp = (size_t)p * p;
     dim3 grid(ew_blocks(pp, M), M);
+    gg_count_launch(1);
     build_w_kernel<<<grid, EW_THREADS, 0, st>>>(Theta, L, X, S, nk, ctrl, mpp, pp, W);
     GG_CHECK_LAUNCH();
     return 0;
@@ -654,8 +722,10 @@ int gg_launch_prox_sgl(const double* Omega, const double* Omega_prev, const doub
         if (Mblk <= 0 || p % Mblk != 0) return -1;
         const int nbk = p / Mblk;
         dim3 gn((nbk * nbk + 7) / 8, M);
+        gg_count_launch(1);
         fsgl_block_norm_kernel<<<gn, 256, 0, st>>>(Omega, L, X, ctrl, p, Mblk, blk_nrm);
     }
+    gg_count_launch(1);
     prox_sgl_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, lam, lam_mat, p, partials,
                                                  pvec, blk_nrm, Mblk);
     GG_CHECK_LAUNCH();
@@ -668,6 +738,7 @@ int gg_launch_dual_update(double* X, const double* Omega, const double* Omega_pr
 {
     const size_t pp = (size_t)p * p;
     dim3 grid(gg_sgl_nparts(p, M), M);
+    gg_count_launch(1);
     dual_update_kernel<<<grid, EW_THREADS, 0, st>>>(X, Omega, Omega_prev, Theta, L, ctrl, mpp, pp, sgl_order, partials);
     GG_CHECK_LAUNCH();
     return 0;
@@ -689,6 +760,7 @@ static int launch_prox_mgl_t(const double* Omega, const double* Omega_prev, cons
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid(nt, nt);
+    gg_count_launch(1);
     kern<<<grid, PT * PT, smem, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials);
     GG_CHECK_LAUNCH();
     return 0;
@@ -710,6 +782,7 @@ int gg_launch_prox_mgl(const double* Omega, const double* Omega_prev, const doub
 int gg_launch_stop_update(const double* partials, int nparts, double* ctrl, double* hist, int hist_cap,
                           const double* pdim, double tol, double rtol, int update_rho, int nprob, cudaStream_t st)
 {
+    gg_count_launch(1);
     stop_update_kernel<<<nprob, 256, 0, st>>>(partials, nparts, ctrl, hist, hist_cap, pdim, tol, rtol, update_rho);
     GG_CHECK_LAUNCH();
     return 0;
@@ -719,9 +792,11 @@ int gg_launch_scale_pending(double* X, double* ctrl, int M, int p, int mpp, cuda
 {
     const size_t pp = (size_t)p * p;
     dim3 grid(ew_blocks(pp, M), M);
+    gg_count_launch(1);
     scale_pending_kernel<<<grid, EW_THREADS, 0, st>>>(X, ctrl, mpp, pp);
     GG_CHECK_LAUNCH();
     const int nprob = M / mpp;
+    gg_count_launch(1);
     reset_xscale_kernel<<<(nprob + 127) / 128, 128, 0, st>>>(ctrl, nprob);
     GG_CHECK_LAUNCH();
     return 0;
@@ -732,6 +807,7 @@ extern "C" int gg_objective_nparts(int p) { return ew_blocks((size_t)p * p, 1); 
 int gg_launch_objective(const double* Omega, const double* S, const double* Theta, double l1, double l2, int reg,
                         int K, int p, double* partials, cudaStream_t st)
 {
+    gg_count_launch(1);
     objective_kernel<<<gg_objective_nparts(p), EW_THREADS, 0, st>>>(Omega, S, Theta, l1, l2, reg, K, p, partials);
     GG_CHECK_LAUNCH();
     return 0;
@@ -740,6 +816,7 @@ int gg_launch_objective(const double* Omega, const double* S, const double* Thet
 int gg_launch_asym_max(const double* A, int M, int p, double* out, cudaStream_t st)
 {
     dim3 grid(gg_sgl_nparts(p, M), M);
+    gg_count_launch(1);
     asym_max_kernel<<<grid, EW_THREADS, 0, st>>>(A, p, out);
     GG_CHECK_LAUNCH();
     return 0;
@@ -749,7 +826,29 @@ int gg_launch_add3(const double* Omega, const double* L, const double* X, double
 {
     size_t blocks = (total + EW_THREADS - 1) / EW_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    gg_count_launch(1);
     add3_kernel<<<(unsigned)blocks, EW_THREADS, 0, st>>>(Omega, L, X, V, total);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_pack_bands(const double* Omega, const double* L, const double* X, const double* ctrl, int K_loc, int p,
+                         int world, double* send, cudaStream_t st)
+{
+    dim3 grid(gg_sgl_nparts(p, K_loc), K_loc);
+    gg_count_launch(1);
+    pack_bands_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, L, X, ctrl, p, K_loc, world, send);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_unpack_dual(const double* recv, const double* Omega, const double* Omega_prev, double* X, double* Theta,
+                          double* C, const double* ctrl, int K_loc, int p, int world, double* partials,
+                          cudaStream_t st)
+{
+    dim3 grid(gg_sgl_nparts(p, K_loc), K_loc);
+    gg_count_launch(1);
+    unpack_dual_kernel<<<grid, EW_THREADS, 0, st>>>(recv, Omega, Omega_prev, X, Theta, C, ctrl, p, K_loc, world, partials);
     GG_CHECK_LAUNCH();
     return 0;
 }
@@ -768,9 +867,11 @@ int gg_launch_prox_band(const double* V, double* Theta, const double* ctrl, doub
     if (grid == 0) return 0;
     if (reg == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gg_count_launch(1);
         prox_band_kernel<0><<<grid, T, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gg_count_launch(1);
         prox_band_kernel<1><<<grid, T, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
     }
     GG_CHECK_LAUNCH();
@@ -781,6 +882,7 @@ int gg_launch_ext_theta(const double* Omega, const double* L, const double* X0, 
                         const double* lam1, const double* ctrl, int K, int p, double* Theta, double* C, cudaStream_t st)
 {
     dim3 grid(gg_sgl_nparts(p, K), K);
+    gg_count_launch(1);
     ext_theta_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, L, X0, Lam, X1, lam1, ctrl, p, Theta, C);
     GG_CHECK_LAUNCH();
     return 0;
@@ -792,9 +894,11 @@ int gg_launch_ext_lambda(const double* Theta, const double* X1, const int* G, in
     const size_t total = (size_t)K * p * p;
     size_t blocks = (total + EW_THREADS - 1) / EW_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    gg_count_launch(1);
     ext_z_kernel<<<(unsigned)blocks, EW_THREADS, 0, st>>>(Theta, X1, ctrl, total, Lam);
     GG_CHECK_LAUNCH();
     if (Lg > 0) {
+        gg_count_launch(1);
         ext_group_prox_kernel<<<(Lg + 127) / 128, 128, 0, st>>>(Theta, X1, G, Lg, K, p, lambda2, ctrl, Lam);
         GG_CHECK_LAUNCH();
     }
@@ -806,6 +910,7 @@ int gg_launch_ext_dual(double* X0, double* X1, const double* Omega, const double
                        const int* pvec, int K, int p, double* partials, cudaStream_t st)
 {
     dim3 grid(gg_sgl_nparts(p, K), K);
+    gg_count_launch(1);
     ext_dual_kernel<<<grid, EW_THREADS, 0, st>>>(X0, X1, Omega, Omega_prev, Theta, L, Lam, Lam_prev, ctrl, pvec, p,
                                                  partials);
     GG_CHECK_LAUNCH();

@@ -434,11 +434,13 @@ static int launch_round(double* G, int M, int p, int nb, int round, double tol, 
         auto k = bj_round_kernel<NB2, KC, true>;
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+        gg_count_launch(1);
         k<<<grid, 256, smem, s>>>(G, p, nb, round, tol, tol_in, inner_max, st);
     } else {
         auto k = bj_round_kernel<NB2, KC, false>;
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+        gg_count_launch(1);
         k<<<grid, 256, smem, s>>>(G, p, nb, round, tol, tol_in, inner_max, st);
     }
     GG_CHECK_LAUNCH();
@@ -494,6 +496,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
         if (threads > JS_THREADS) threads = JS_THREADS;
         if (threads < 64) threads = 64;
         const int ne = (p + JS_LP - 1) / JS_LP;
+        gg_count_launch(1);
         if (ne <= 2) jacobi_small_kernel<2><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
         else if (ne <= 4) jacobi_small_kernel<4><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
         else if (ne <= 6) jacobi_small_kernel<6><<<M, threads, smem, s>>>(A, D, p, tol, max_sweeps, ctrl, mpp, sweeps_small, Vwarm);
@@ -518,8 +521,10 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
     const double tol_in = 1.0e-15;
 
     dim3 grows((p + 7) / 8, M);
+    gg_count_launch(1);
     gersh_rows_kernel<<<grows, 256, 0, s>>>(A, p, st.rowlo, st.rowhi);
     GG_CHECK_LAUNCH();
+    gg_count_launch(1);
     gersh_shift_kernel<<<M, 256, 0, s>>>(A, p, st, ctrl, mpp);
     GG_CHECK_LAUNCH();
 
@@ -532,6 +537,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
             else rc = launch_round<128, 16>(A, M, p, nb, r, tol, tol_in, 30, st, s);
             if (rc) return rc;
         }
+        gg_count_launch(1);
         bj_sweep_end_kernel<<<1, 256, 0, s>>>(st, M, quad_tol);
         GG_CHECK_LAUNCH();
         used = sweep + 1;
@@ -544,6 +550,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
             if (h_flag) break;
         }
     }
+    gg_count_launch(1);
     bj_finalize_kernel<<<grows, 256, 0, s>>>(A, D, p, st, ctrl, mpp, vectors);
     GG_CHECK_LAUNCH();
     if (info) info[0] = used;
@@ -570,8 +577,10 @@ int gg_gershgorin_min_impl(const double* A, int M, int p, void* ws, size_t ws_by
     double* rowlo = (double*)ws;
     double* rowhi = (double*)((char*)ws + align_up(sizeof(double) * (size_t)M * p, 256));
     dim3 grows((p + 7) / 8, M);
+    gg_count_launch(1);
     gersh_rows_kernel<<<grows, 256, 0, s>>>(A, p, rowlo, rowhi);
     GG_CHECK_LAUNCH();
+    gg_count_launch(1);
     gersh_min_kernel<<<M, 256, 0, s>>>(rowlo, p, out);
     GG_CHECK_LAUNCH();
     return 0;

@@ -140,6 +140,7 @@ int gg_launch_recon(const double* Vt, const double* D, const double* bnum, const
 {
     const int nt = (p + RT - 1) / RT;
     dim3 grid(nt, nt, M);
+    gg_count_launch(1);
     if ((p & 1) == 0) recon_kernel<true><<<grid, 256, 0, st>>>(Vt, D, bnum, ctrl, mpp, mode, p, Out);
     else recon_kernel<false><<<grid, 256, 0, st>>>(Vt, D, bnum, ctrl, mpp, mode, p, Out);
     GG_CHECK_LAUNCH();

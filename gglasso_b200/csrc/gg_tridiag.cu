@@ -1596,11 +1596,15 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
 #ifdef TR_TIMING
     tw.dbg = (long long*)dw.U;            // U is not used before stage 2; read back by the timing script
 #endif
+    gg_count_launch(1);
     tr_skip_kernel<<<(M + 127) / 128, 128, 0, s>>>(ctrl, mpp, M, skip);
     GG_CHECK_LAUNCH();
     dim3 gz(64, M);
+    gg_count_launch(1);
     tr_zero_kernel<<<gz, 256, 0, s>>>(tw.Vh, nn, skip);
+    gg_count_launch(1);
     tr_zero_kernel<<<gz, 256, 0, s>>>(Q0, nn, skip);
+    gg_count_launch(1);
     tr_zero_kernel<<<dim3(1, M), 256, 0, s>>>(tw.tau, (size_t)n, skip);
     GG_CHECK_LAUNCH();
 
@@ -1626,6 +1630,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 const int thr = len <= 2048 ? 256 : 512;
                 cfg.gridDim = dim3(M); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = 0;
                 cudaError_t e;
+                gg_count_launch(1);
                 if (len <= 512) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<2, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
                 else if (len <= 1024) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<4, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
                 else if (len <= 2048) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
@@ -1639,6 +1644,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 const int t = n - j - 1;
                 const int nt = (t + SV_T - 1) / SV_T;
                 cfg.gridDim = dim3(nt * (nt + 1) / 2, M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+                gg_count_launch(1);
                 cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, kb, write, tw, (const int*)skip, nt);
                 if (e != cudaSuccess) return (int)e;
             }
@@ -1654,6 +1660,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 tattr = true;
             }
             cfg.gridDim = dim3(M); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = tsm;
+            gg_count_launch(1);
             cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip);
             if (e != cudaSuccess) return (int)e;
         }
@@ -1682,8 +1689,11 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     const bool use_big = npanels > 0 && which != 4 && bt_big && n >= BB_MIN;
     if (use_big) {
         const int nt64 = (n + BB_T - 1) / BB_T;
+        gg_count_launch(1);
         bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, n, npb, Gb, skip);
+        gg_count_launch(1);
         bb_x_kernel<<<dim3(npb, M), 8 * BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), s>>>(Gb, tw.tau, n, npb, Xb, skip);
+        gg_count_launch(1);
         bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, Xb, n, npb, Vp, skip);
         GG_CHECK_LAUNCH();
     }
@@ -1691,12 +1701,16 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     // ---- stage 2 ----
     // buffers: leaves write Qt into buf[L & 1 ? ...]; arrange so that the root lands in A.
     double* qbuf[2] = {A, Q0};           // level l merge reads qbuf[(l+1)&1], writes qbuf[l&1]; root (l=0) -> A
+    gg_count_launch(1);
     tr_zero_kernel<<<gz, 256, 0, s>>>(A, nn, skip);
+    gg_count_launch(1);
     dc_scale_kernel<<<M, 256, 0, s>>>(tw.d, tw.e, n, scale, skip);
     if (L > 0) {
         const int nsplit = (1 << L) - 1;
+        gg_count_launch(1);
         dc_tear_kernel<<<dim3((nsplit + 127) / 128, M), 128, 0, s>>>(tw.d, tw.e, n, L, skip);
     }
+    gg_count_launch(1);
     dc_leaf_kernel<<<dim3(1 << L, M), 128, 0, s>>>(tw.d, tw.e, n, L, dw.lam[L & 1], qbuf[L & 1], skip);
     GG_CHECK_LAUNCH();
     if (dbg_stage && dbg_nonfinite(dw.lam[L & 1], M, n, n, s)) return -14;
@@ -1715,11 +1729,16 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         if (psm > 200 * 1024) return -4;
         const double* Qin = qbuf[(l + 1) & 1];
         double* Qout = qbuf[l & 1];
+        gg_count_launch(1);
         dc_prepare_kernel<<<dim3(nodes, M), 1024, psm, s>>>(tw.e, n, l, dw.lam[(l + 1) & 1], dw.lam[l & 1],
                                                             (double*)Qin, Qout, dw, skip);
+        gg_count_launch(1);
         dc_secular_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, sizeof(double) * 2 * Nmax, s>>>(n, l, dw.lam[l & 1], dw, skip);
+        gg_count_launch(1);
         dc_zhat_kernel<<<dim3((Nmax + ZH_C - 1) / ZH_C, nodes, M), ZH_C * ZH_G, 0, s>>>(n, l, dw, skip);
+        gg_count_launch(1);
         dc_vectors_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, 0, s>>>(n, l, dw, skip);
+        gg_count_launch(1);
         dc_gemm_kernel<<<dim3((Nmax + DG_T - 1) / DG_T, (Nmax + DG_T - 1) / DG_T, nodes * M), 256, 0, s>>>(n, l, Qin, Qout, dw, skip);
         GG_CHECK_LAUNCH();
         if (dbg_stage) {
@@ -1727,6 +1746,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         }
     }
     // eigenvalues of the root are in lam[0]; eigenvectors of T (rows) in A
+    gg_count_launch(1);
     dc_unscale_kernel<<<dim3(4, M), 256, 0, s>>>(dw.lam[0], scale, n, D, skip);
     if (stop_after == 2) return 0;
 
@@ -1737,11 +1757,15 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         const int nt64 = (n + BB_T - 1) / BB_T;
         for (int P = npb - 1; P >= 0; --P) {
             const int len = n - (P * BB_NB + 1);
+            gg_count_launch(1);
             bb_y_kernel<<<dim3(BB_NB / BB_T, nt64, M), 256, 0, s>>>(A, tw.Vh, n, P, Yb, skip);
+            gg_count_launch(1);
             bb_upd_kernel<<<dim3((len + BB_T - 1) / BB_T, nt64, M), 256, 0, s>>>(A, Vp, Yb, n, P, skip);
         }
     } else if (npanels > 0 && which != 4) {
+        gg_count_launch(1);
         bt_larft_kernel<<<dim3(npanels, M), 256, 0, s>>>(tw.Vh, tw.tau, n, Tm, npanels, skip);
+        gg_count_launch(1);
         bt_apply_kernel<<<dim3((n + BT_R - 1) / BT_R, M), 256, 0, s>>>(A, tw.Vh, Tm, n, npanels, skip);
     }
     GG_CHECK_LAUNCH();

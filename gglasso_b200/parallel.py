@@ -33,6 +33,20 @@ def partition(n, parts):
     return out
 
 
+def band_layout_index(K_loc, p, world):
+    """index map of the all-to-all buffers written by gg_pack_bands / read by gg_unpack_dual: element (k, r, c) of
+    this rank's (K_loc, p, p) stack sits at ``idx[k, r, c]`` of the flat buffer -- band d = partition(p, world)[d] of
+    all local instances is one contiguous block [K_loc][rows_d][p].  Host-side statement of the CUDA layout (tests)."""
+    idx = np.empty((K_loc, p, p), dtype=np.int64)
+    col = np.arange(p)
+    for lo, hi in partition(p, world):
+        rows = hi - lo
+        for k in range(K_loc):
+            r = np.arange(lo, hi)
+            idx[k, lo:hi, :] = K_loc * p * lo + ((k * rows + (r - lo)) * p)[:, None] + col[None, :]
+    return idx
+
+
 class KShard:
     """layout bookkeeping for a K-sharded (K_total, p, p) stack."""
 
@@ -129,27 +143,40 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
     st.pdim.fill_(K_total * ((p ** 2 + p) / 2))
     lib, stream = st.lib, st.stream
     regi = 0 if reg == "GGL" else 1
-    V = torch.empty_like(st.S)
     nparts = lib.gg_sgl_nparts(p, K_loc) * K_loc
     partials = torch.zeros((nparts, NPART), dtype=torch.float64, device=st.dev)
     tot = torch.zeros((1, NPART), dtype=torch.float64, device=st.dev)
-    total = K_loc * p * p
+    # all-to-all buffers, allocated once: `send` = this rank's instances cut into row bands, `band` = this rank's row
+    # band of ALL instances, `tband` = Theta on that band (kept across iterations: once the done flag is set the
+    # kernels are no-ops and Theta stays what the last executed iteration produced), `back` = Theta of the local
+    # instances, band by band.  With one rank the exchanges are the identity and the buffers alias.
+    loc_n, band_n = K_loc * p * p, K_total * sh.nb * p
+    send = torch.empty(loc_n, dtype=torch.float64, device=st.dev)
+    band = torch.empty(band_n, dtype=torch.float64, device=st.dev) if sh.world > 1 else send
+    tband = torch.zeros(band_n, dtype=torch.float64, device=st.dev)
+    back = torch.empty(loc_n, dtype=torch.float64, device=st.dev) if sh.world > 1 else tband
+    loc_split = [K_loc * (hi - lo) * p for lo, hi in sh.rparts]
+    band_split = [(khi - klo) * sh.nb * p for klo, khi in sh.kparts]
 
     for it in range(max_iter):
         st.omega_step()
-        _lib.check(lib.gg_add3(_p(st.Omega_new), _p(st.L), _p(st.X), _p(V), total, stream), "gg_add3")
-        Vb = sh.to_band(V)
-        Tb = torch.empty_like(Vb)
-        _lib.check(lib.gg_prox_band(_p(Vb), _p(Tb), _p(st.ctrl), float(lambda1), float(lambda2), regi, K_total, sh.nb,
-                                    p, sh.r_lo, stream), "gg_prox_band")
-        st.Theta = sh.from_band(Tb)
+        _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), K_loc, p, sh.world, _p(send),
+                                     stream), "gg_pack_bands")
+        if sh.world > 1:
+            dist.all_to_all_single(band, send, band_split, loc_split, group=sh.group)
+        _lib.check(lib.gg_prox_band(_p(band), _p(tband), _p(st.ctrl), float(lambda1), float(lambda2), regi, K_total,
+                                    sh.nb, p, sh.r_lo, stream), "gg_prox_band")
+        if sh.world > 1:
+            dist.all_to_all_single(back, tband, loc_split, band_split, group=sh.group)
+        # Theta back in instance layout, fused with the dual update and the residual sums (non-latent) or with
+        # C = Theta - X - Omega for the L step (latent)
+        _lib.check(lib.gg_unpack_dual(_p(back), _p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta),
+                                      _p(st.W) if latent else None, _p(st.ctrl), K_loc, p, sh.world, _p(partials),
+                                      stream), "gg_unpack_dual")
         if latent:
-            # C = Theta - X - Omega, L = prox_rank_norm(C)  (per instance, local)
-            torch.sub(st.Theta, st.X, out=st.W)
-            st.W.sub_(st.Omega_new)
             st.l_step()
-        _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L), _p(st.ctrl),
-                                      K_loc, p, K_loc, 0, _p(partials), stream), "gg_dual_update")
+            _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L),
+                                          _p(st.ctrl), K_loc, p, K_loc, 0, _p(partials), stream), "gg_dual_update")
         torch.sum(partials, 0, keepdim=True, out=tot)
         sh.allreduce_sum(tot)
         _lib.check(lib.gg_stop_update(_p(tot), 1, _p(st.ctrl), _p(st.hist), st.hist_cap, _p(st.pdim), tol, rtol,

@@ -72,11 +72,6 @@ def ADMM_MGL(S: np.ndarray,
     # iterates stay symmetric, so the check is done once on the inputs -- on the device, after the upload
     # (run_admm(check_symmetric=True)), not with host-side temporaries.
 
-    if K > _K_TILE_MAX and stopping_criterion == 'boyd' and not measure:
-        # the fused tile-pair prox keeps K x 272 doubles per CTA in shared memory; beyond that the row-band
-        # variant (shared with the multi-GPU path, block size adapts to K) takes over
-        return _large_K(S, lambda1, lambda2, reg, Omega_0, Theta_0, X_0, nk, tol, rtol, update_rho, rho, max_iter,
-                        verbose, latent, mu, K, p)
     st, res = run_admm('mgl', S, Omega_0, Theta_0, X_0, lambda1=float(lambda1), lambda2=float(lambda2), reg=reg,
                        rho=float(rho), max_iter=int(max_iter), tol=tol, rtol=rtol,
                        stopping_criterion=stopping_criterion, update_rho=update_rho, verbose=verbose,
@@ -116,20 +111,3 @@ def ADMM_MGL(S: np.ndarray,
     else:
         info = {'status': status}
     return sol, info
-
-
-_K_TILE_MAX = 90
-
-
-def _large_K(S, lambda1, lambda2, reg, Omega_0, Theta_0, X_0, nk, tol, rtol, update_rho, rho, max_iter, verbose,
-             latent, mu, K, p):
-    from ..parallel import run_admm_mgl_dist
-    st, info = run_admm_mgl_dist(S, float(lambda1), float(lambda2), reg, Omega_0, K_total=K, Theta_0_local=Theta_0,
-                                 X_0_local=X_0, n_samples=None if nk is None else nk, tol=tol, rtol=rtol,
-                                 update_rho=update_rho, rho=float(rho), max_iter=int(max_iter), verbose=verbose,
-                                 latent=latent, mu1_local=mu, group=False)
-    print(f"ADMM terminated after {info['iterations']} iterations with status: {info['status']}.")
-    Omega = st.final_omega([info["iterations"]])
-    sol = {'Omega': to_host(Omega), 'Theta': to_host(st.Theta),
-           'L': to_host(st.L) if latent else np.zeros((K, p, p)), 'X': to_host(st.X)}
-    return sol, {'status': info['status']}

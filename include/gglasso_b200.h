@@ -35,6 +35,10 @@ extern "C" {
 
 int gg_version(void);
 
+/* number of kernels this library has launched in the calling process so far (monotonic; bench.py reports the
+ * difference over its timed region as `gpu_launches`).  New; no reference counterpart. */
+long long gg_launch_count(void);
+
 /* W = Theta - L - X - (n_k/rho) S ; also folds the pending rescale of X (rho_old/rho_new) into X.
  * reference: src/gglasso/solver/admm_solver.py:180,236 ; single_admm_solver.py:163,205.
  * L may be NULL (non-latent); nk may be NULL (all ones) or a device array (M). */
@@ -106,6 +110,18 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
  * (L may be NULL), and the cross-instance prox on a row band: V, Theta are (K, nb, p) slabs holding global rows
  * row0..row0+nb-1 of all K instances (after the all-to-all re-tile).  Same prox as gg_prox_mgl. */
 int gg_add3(const double* Omega, const double* L, const double* X, double* V, size_t total, void* stream);
+/* The two re-tile passes of the K-sharded solve, fused with their neighbours (no torch.cat / strided copies on the
+ * hot path).  The p rows are cut into `world` contiguous bands (first p % world bands one row longer); band d of the
+ * K_loc local instances is the contiguous block [K_loc][rows_d][p] at offset K_loc*p*lo_d of `send` / `recv`, i.e.
+ * exactly the split layout of the two all-to-all exchanges.
+ *   gg_pack_bands : send = (Omega + L) + X   (admm_solver.py:190 argument of prox_p), L may be NULL
+ *   gg_unpack_dual: Theta (instance layout) from `recv`; C == NULL: X += Omega - Theta and the five residual partial
+ *                   sums (admm_solver.py:208,316-331; partials (K_loc * gg_sgl_nparts(p,K_loc), 5));
+ *                   C != NULL (latent): C = Theta - X - Omega (admm_solver.py:197), dual update follows the L step. */
+int gg_pack_bands(const double* Omega, const double* L, const double* X, const double* ctrl, int K_loc, int p, int world,
+                  double* send, void* stream);
+int gg_unpack_dual(const double* recv, const double* Omega, const double* Omega_prev, double* X, double* Theta,
+                   double* C, const double* ctrl, int K_loc, int p, int world, double* partials, void* stream);
 int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lambda1, double lambda2, int reg,
                  int K, int nb, int p, int row0, void* stream);
 

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gglasso_b200.parallel import KShard, assign_blocks, block_SGL_dist, ebic_mgl, grid_search_dist, partition
+from gglasso_b200.parallel import (KShard, assign_blocks, band_layout_index, block_SGL_dist, ebic_mgl, grid_search_dist,
+                                    partition)
 
 
 def _free_port():
@@ -183,3 +184,47 @@ def test_block_sgl_distributed_gloo_ws2_matches_oracle():
         np.testing.assert_allclose(got[1], ref["Theta"], atol=1e-12)
         np.testing.assert_allclose(got[2], ref["Omega"], atol=1e-12)
         np.testing.assert_allclose(got[3], ref["X"], atol=1e-12)
+
+
+def _packed_exchange_worker(rank, world, port, K, p, q):
+    """the exchange of run_admm_mgl_dist with its preallocated buffers: the layout gg_pack_bands writes
+    (band_layout_index) is exactly the split layout of the two all_to_all_single calls"""
+    _init(rank, world, port)
+    try:
+        full = torch.arange(K * p * p, dtype=torch.float64).view(K, p, p)
+        sh = KShard(K, p)
+        loc = full[sh.k_lo:sh.k_hi].clone()
+        idx = torch.from_numpy(band_layout_index(sh.K_loc, p, world)).view(-1)
+        send = torch.empty(sh.K_loc * p * p, dtype=torch.float64)
+        send[idx] = loc.view(-1)                                   # what gg_pack_bands does
+        band = torch.empty(K * sh.nb * p, dtype=torch.float64)
+        loc_split = [sh.K_loc * (hi - lo) * p for lo, hi in sh.rparts]
+        band_split = [(khi - klo) * sh.nb * p for klo, khi in sh.kparts]
+        dist.all_to_all_single(band, send, band_split, loc_split)
+        ok1 = torch.equal(band.view(K, sh.nb, p), full[:, sh.r_lo:sh.r_hi, :])
+        back = torch.empty(sh.K_loc * p * p, dtype=torch.float64)
+        dist.all_to_all_single(back, band * 3.0, loc_split, band_split)
+        ok2 = torch.equal(back[idx].view(sh.K_loc, p, p), 3.0 * loc)   # what gg_unpack_dual reads
+        q.put((rank, bool(ok1), bool(ok2)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("K,p", [(5, 7), (20, 16), (3, 2)])
+def test_packed_band_exchange_gloo_ws2(K, p):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_packed_exchange_worker, args=(r, 2, port, K, p, q)) for r in range(2)]
+    [pr.start() for pr in procs]
+    res = [q.get(timeout=120) for _ in range(2)]
+    [pr.join(60) for pr in procs]
+    assert all(ok1 and ok2 for _, ok1, ok2 in res), res
+
+
+def test_band_layout_index_is_a_permutation():
+    for K_loc, p, world in [(1, 1, 1), (3, 10, 4), (2, 7, 7), (5, 9, 2), (10, 16, 8)]:
+        idx = band_layout_index(K_loc, p, world)
+        assert np.array_equal(np.sort(idx.reshape(-1)), np.arange(K_loc * p * p))
+        if world == 1:
+            assert np.array_equal(idx.reshape(-1), np.arange(K_loc * p * p))
