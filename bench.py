@@ -5,8 +5,9 @@
 Metric (BASELINE.json): ADMM iterations/sec AND time-to-tolerance for the fused multiple graphical lasso K=20, p=1000
 (cfg3: ADMM_MGL, reg='FGL', lambda1=0.05, lambda2=0.01, N=2000 samples per instance, rho=1, update_rho=True), plus the
 10x10 lambda grid (cfg4) as a secondary block.  Inputs come from the REFERENCE's own seeded generators
-(time_varying_power_network(1000, 20, 10, seed=1234) + sample_covariance_matrix(N=2000, seed=1234), run from oracle/_ref
-through oracle/ref_inputs.py, cached under /tmp) -- input preparation only, outside every timed region.
+(time_varying_power_network(1000, 20, 10, seed=1234) + the sample_covariance_matrix recipe with N=2000, seed=1234 and a
+host-independent Cholesky sampler, run from oracle/_ref through oracle/ref_inputs.py, cached under /tmp) -- input
+preparation only, outside every timed region.
 A "step" is one ADMM iteration over the whole (K,p,p) stack.
 
   value        iterations/sec with S resident in HBM, CUDA events around exactly --steps iterations (stopping test
@@ -375,7 +376,8 @@ def fixture_check(Theta, k_lo, k_hi, p, world):
     mine = Theta.reshape(-1)
     return {"pattern_identical": bool(np.array_equal(mine != 0, ref != 0)),
             "err2": float(np.sum((mine - ref) ** 2)), "ref2": float(np.sum(ref ** 2)),
-            "fixture": "tests/golden/cfg3_fgl_full.npz (real reference, 11 iterations, objective 11752.409197493562)"}
+            "fixture": f"tests/golden/cfg3_fgl_full.npz (real reference, {len(g['objective'])} iterations, "
+                       f"objective {float(g['objective'][-1])!r})"}
 
 
 def grid_bench(world, rank, barrier, max_over_ranks):

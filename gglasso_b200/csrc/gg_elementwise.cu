@@ -231,8 +231,17 @@ prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
 {
     extern __shared__ double ysm[];                 // K * PSLOT
     __shared__ double scratch[GG_NPART * 32];
-    const int I = blockIdx.y, J = blockIdx.x;
-    if (I > J) return;
+    // Only tile pairs I <= J are launched, in super-tile order: blockIdx.x = 16 * (super-tile pair) + (a, b), so that
+    // CTAs which are resident together cover 4 x 4 neighbouring tiles.  Each k-slice of a 16 x 16 tile is a set of
+    // 128-byte row segments 8 MB apart; with neighbouring tiles in flight both the tile side and the mirror side
+    // touch 512 contiguous bytes per matrix row, which keeps DRAM pages open (row-major order gave that to the tile
+    // side only).
+    const int nt = (p + PT - 1) / PT, nst = (nt + 3) >> 2;
+    int sp = blockIdx.x >> 4, SI = 0;
+    while (sp >= nst - SI) { sp -= nst - SI; ++SI; }
+    const int SJ = SI + sp;
+    const int I = 4 * SI + ((blockIdx.x >> 2) & 3), J = 4 * SJ + (blockIdx.x & 3);
+    if (I > J || J >= nt) return;
     if (ctrl[GG_C_DONE] != 0.0) return;
     const double inv_rho = 1.0 / ctrl[GG_C_RHO];
     const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
@@ -326,7 +335,7 @@ prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
     if (!LATENT) {
         gg_block_sum<GG_NPART>(acc, scratch);
         if (threadIdx.x == 0) {
-            double* out = partials + ((size_t)I * gridDim.x + J) * GG_NPART;
+            double* out = partials + ((size_t)I * nt + J) * GG_NPART;
 #pragma unroll
             for (int q = 0; q < GG_NPART; ++q) out[q] = acc[q];
         }
@@ -759,7 +768,8 @@ static int launch_prox_mgl_t(const double* Omega, const double* Omega_prev, cons
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid(nt, nt);
+    const int nst = (nt + 3) / 4;
+    dim3 grid(16 * (nst * (nst + 1) / 2));
     gg_count_launch(1);
     kern<<<grid, PT * PT, smem, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials);
     GG_CHECK_LAUNCH();

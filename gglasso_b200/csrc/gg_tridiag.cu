@@ -420,7 +420,7 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
 // tile), then runs the unblocked Householder steps in place.
 #define TR_TAIL 144
 __global__ void __launch_bounds__(512)
-tr_tail_kernel(const double* __restrict__ A, int n, int js, TrWs ws, const int* __restrict__ skip)
+tr_tail_kernel(const double* __restrict__ A, int n, int js, TrWs ws, const int* __restrict__ skip, int pending)
 {
     extern __shared__ double tsm[];
     const int m = blockIdx.x;
@@ -439,7 +439,7 @@ tr_tail_kernel(const double* __restrict__ A, int n, int js, TrWs ws, const int* 
     double* dd = ws.d + (size_t)m * n;
     double* ee = ws.e + (size_t)m * n;
     double* Vh = ws.Vh + (size_t)m * n * n;
-    const bool pend = js >= 1;
+    const bool pend = js >= 1 && pending;      // blocked path: the trailing block is fully updated, nothing pending
     if (pend) {
         const double* y = ws.y + (size_t)m * n;
         const double* vprev = ws.vbuf + ((size_t)m * 2 + ((js + 1) & 1)) * n;
@@ -521,6 +521,8 @@ tr_tail_kernel(const double* __restrict__ A, int n, int js, TrWs ws, const int* 
         __syncthreads();
     }
 }
+
+#include "gg_sytrd_blocked.cuh"
 
 // =============================================================================================
 // stage 2: divide & conquer on the tridiagonal matrices
@@ -1542,6 +1544,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += al(sizeof(double) * (size_t)M);                  // scale
     b += 2 * al(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);   // G, X of the blocked back-transformation
     if (n >= BB_MIN) b += al(sizeof(double) * M * nn);   // V' = X V
+    b += al(sizeof(double) * sytrd_blocked_ws_doubles(M, n));   // W panel of the blocked tridiagonalisation
     return b;
 }
 
@@ -1590,6 +1593,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     double* Gb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
     double* Xb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
     double* Vp = (n >= BB_MIN) ? (double*)take(sizeof(double) * M * nn) : nullptr;
+    double* Wpanel = (double*)take(sizeof(double) * sytrd_blocked_ws_doubles(M, n));
     static int stop_after = -1;
     if (stop_after < 0) { const char* ev = getenv("GG_TR_STOP"); stop_after = ev ? atoi(ev) : 0; }
 
@@ -1621,10 +1625,20 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         static int no_pdl = -1;
         if (no_pdl < 0) { const char* ev = getenv("GG_NO_PDL"); no_pdl = ev ? atoi(ev) : 0; }
         cfg.numAttrs = no_pdl ? 0 : 1;
-        const int js = (which == 1 || which == 2) ? n : (n > TR_TAIL ? n - TR_TAIL : 0);   // tail takes over at column js
+        static int tr_old = -1;
+        if (tr_old < 0) { const char* ev = getenv("GG_TR_OLD"); tr_old = ev ? atoi(ev) : 0; }
+        // blocked path (cluster panel kernel + DMMA rank-2k update) for TR_TAIL < n <= PB_NMAX; the per-column
+        // BLAS-2 chain below remains for larger matrices and as a cross-check (GG_TR_OLD=1)
+        const bool use_blocked = !tr_old && n > TR_TAIL && n <= PB_NMAX;
+        const int js = use_blocked ? n - TR_TAIL
+                                   : ((which == 1 || which == 2) ? n : (n > TR_TAIL ? n - TR_TAIL : 0));   // tail takes over at column js
+        if (use_blocked) {
+            const int rc = sytrd_blocked_run(A, n, M, js, tw, Wpanel, skip, s, (which == 1 || which == 2) ? which : 0);
+            if (rc != 0) return rc;
+        }
         const int lazy_q = gg_tr_lazy_depth();
         int kb = 0;                                   // pairs kb..j-1 are pending at step j
-        for (int j = 0; j < js; ++j) {
+        for (int j = 0; j < js && !use_blocked; ++j) {
             if (which != 2) {
                 const int len = n - j;
                 const int thr = len <= 2048 ? 256 : 512;
@@ -1650,7 +1664,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
             }
             if (write) kb = j;
         }
-        if (js < n) {
+        if (js < n && !(use_blocked && (which == 1 || which == 2))) {
             const int ts = n - js;
             const size_t tsm = sizeof(double) * ((size_t)ts * (ts | 1) + 3 * ts + 64 + 4);
             static bool tattr = false;
@@ -1661,7 +1675,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
             }
             cfg.gridDim = dim3(M); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = tsm;
             gg_count_launch(1);
-            cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip, use_blocked ? 0 : 1);
             if (e != cudaSuccess) return (int)e;
         }
     }

@@ -3,8 +3,11 @@
 (tests/golden/make_golden_large.py).  north_star bar: Theta/Omega/X within 1e-8 relative Frobenius per iteration,
 final objective within 1e-6 relative, identical sparsity pattern at tol=1e-7.
 
-The inputs are regenerated here (they are too large to commit); their fingerprints are compared with the ones recorded
-next to the fixtures, so a host whose LAPACK rounds differently shows up as a reported deviation, not as a silent one.
+The inputs are regenerated here (they are too large to commit) with the host-independent sampler of
+oracle/ref_inputs.py; their fingerprints are compared with the ones recorded next to the fixtures, so a host whose
+LAPACK rounds differently shows up as a reported deviation, not as a silent one.  (With the reference's default SVD
+sampler the survey's container run gave objective 11752.409197493562 / nnz 48024 at cfg3; the Cholesky-sampled input
+of the same generators and seeds gives 11752.787900092353 / 47854 -- tests/golden/cfg3_fgl_full.npz.)
 """
 import contextlib
 import io
@@ -83,7 +86,7 @@ def test_cfg3_full_solve_vs_reference_trajectory(golden):
     (sol, info), out = _quiet(ADMM_MGL, S, 0.05, 0.01, "FGL", Om0, tol=1e-7, rtol=1e-7, measure=True)
     assert info["status"] == str(g["status"]) and f"ADMM terminated after {n} iterations" in out
     np.testing.assert_allclose(info["objective"], g["objective"], rtol=1e-6)
-    assert abs(info["objective"][-1] - 11752.409197493562) <= 1e-6 * 11752.409197493562
+    assert abs(info["objective"][-1] - float(g["objective"][-1])) <= 1e-6 * abs(float(g["objective"][-1]))
     np.testing.assert_allclose(info["residual"], g["residual"], rtol=1e-7, atol=1e-12)
     Theta_ref = _dense(S.shape, g["theta_idx"], g["theta_val"])
     assert np.array_equal(np.flatnonzero(sol["Theta"].reshape(-1)), g["theta_idx"]), "sparsity pattern differs"
