@@ -267,6 +267,7 @@ def main():
 
     # ---------------- kernel-level roofline of the dominant kernel (rank 0) ----------------------------------------
     roof = kernel_roofline(st, ms / steps) if rank == 0 else None
+    blocked = blocked_path_numbers(st, ms / steps) if (rank == 0 and world == 1) else None
     del st
 
     # ---------------- end to end through the public API (host buffers), `steps` iterations -------------------------
@@ -339,11 +340,11 @@ def main():
                 "config": {"workload": WORKLOAD, **CFG,
                            "l2": "inputs larger than L2 (each (K,p,p) FP64 array is 160 MB; >10 arrays per step)",
                            "K_total": K, "partition": shard, "input_fingerprint_dev": in_dev,
-                           "eigh": "blocked sytrd (cluster panel kernel + DMMA syr2k) + divide&conquer + ormtr, hand-written"},
+                           "eigh": "sytrd (per-column chain, lazy write-back) + divide&conquer + blocked ormtr, hand-written"},
                 "e2e": {"value": e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "time_to_tol": ttt_info, "parity": check,
                 "gpu_launches": launches * world, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
-                "weak": weak, "grid": None}
+                "weak": weak, "blocked_sytrd": blocked, "grid": None}
 
     # secondary measurement, last: the headline line above is complete before it starts and is printed even if the
     # grid run fails (single process; with several ranks a failure surfaces through torchrun)
@@ -411,8 +412,12 @@ def grid_bench(world, rank, barrier, max_over_ranks):
 
 
 def kernel_roofline(st, ms_per_step):
-    """Dominant kernel of the step, timed live with CUDA events on the launch stream through gg_sytrd_profile, which
-    issues exactly the launches of the selected kernel class of one tridiagonalisation of the batch."""
+    """Dominant kernel of the step: tr_symv_kernel (trailing-matrix pass of the Householder
+    tridiagonalisation: applies the pending rank-2 update to the upper triangle and accumulates the full
+    symmetric A*v from that one half-matrix sweep; HBM/L2 bound).
+    Timed live with CUDA events on the launch stream through gg_sytrd_profile(which=2), which issues
+    exactly the (p-1) symv launches of one eigendecomposition of the batch."""
+    import ctypes
     import torch
     from gglasso_b200 import _lib
     from gglasso_b200._engine import _p
@@ -461,7 +466,68 @@ def kernel_roofline(st, ms_per_step):
             "avg_ms_per_launch": times[2] / n_launch,
             "algorithmic_bytes_per_launch_avg": total_bytes / n_launch,
             "symv_ms_per_step": times[2], "col_kernels_ms_per_step": times[1], "sytrd_ms_per_step": times[0],
-            "share_of_step": times[2] / ms_per_step}
+            "share_of_step": times[2] / ms_per_step,
+            "note": "trailing blocks shrink from 160 MB to 0 over the launches; blocks below ~126 MB total are L2 resident, "
+                    "so late launches can exceed the HBM figure"}
+
+
+def blocked_path_numbers(st, ms_per_step):
+    """Dominant kernel of the step: sytrd_panel_kernel, the panel kernel of the blocked tridiagonalisation (one launch
+    per 16 columns, one thread-block cluster per matrix; per column every cluster streams the upper triangle of its
+    trailing matrix once -- from shared memory, L2 or HBM -- and exchanges partial results over distributed shared
+    memory).  Timed live with CUDA events on the launch stream through gg_sytrd_profile(which=1), which issues exactly
+    the panel launches of one tridiagonalisation of the batch; which=2 issues the DMMA rank-2k updates, which=0 both
+    plus the shared-memory tail."""
+    import torch
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import _p
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs")
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    if hbm is None:
+        hbm, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    lib = _lib.load()
+    M, p = st.M, st.p
+    stream = torch.cuda.current_stream().cuda_stream
+    times = {}
+    os.environ["GG_TR_BLOCKED"] = "1"        # (read per call by the library) every column below the tail on the blocked path
+    for which in (1, 2, 0):
+        best = 1e30
+        for rep in range(3):
+            W = (st.Theta - st.X - st.S).contiguous()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = lib.gg_sytrd_profile(_p(W), _p(st.eig.D), M, p, _p(st.eig.ws), st.eig.ws_bytes, which, stream)
+            b.record()
+            torch.cuda.synchronize()
+            assert rc == 0, rc
+            if rep >= 1:
+                best = min(best, a.elapsed_time(b))
+        times[which] = best
+    os.environ.pop("GG_TR_BLOCKED", None)
+    tail, nb = 144, 16
+    ncols = p - tail
+    n_launch = (ncols + nb - 1) // nb
+    # algorithmic bytes: column j reads the UPPER TRIANGLE of the t x t trailing block (t = p-j-1) of each of the M
+    # matrices once, 8 * t(t+1)/2 bytes (SURVEY 8(d): a streaming FP64 pass moves 8 B per element read)
+    total_bytes = sum(8.0 * M * (p - j - 1) * (p - j) / 2 for j in range(ncols))
+    achieved = total_bytes / (times[1] * 1e-3) / 1e9
+    flops_syr2k = sum(2.0 * M * (2 * nb) * (p - j0 - min(nb, ncols - j0)) ** 2 / 2 for j0 in range(0, ncols, nb))
+    return {"what": "alternative blocked tridiagonalisation (not the default: the per-column chain is faster at this shape), timed the same way", "bound": "hbm", "kernel": "sytrd_panel_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+            "launches_per_step": n_launch, "columns_per_launch": nb, "avg_ms_per_launch": times[1] / n_launch,
+            "algorithmic_bytes_per_launch_avg": total_bytes / n_launch,
+            "panel_ms_per_step": times[1], "syr2k_ms_per_step": times[2], "sytrd_ms_per_step": times[0],
+            "syr2k_tflops": flops_syr2k / (times[2] * 1e-3) / 1e12,
+            "share_of_step": times[1] / ms_per_step,
+            "note": "latency bound, not bandwidth bound: two cluster barriers and ~10 dependent shared-memory phases per "
+                    "column; part of every strip is resident in shared memory or pinned in L2, so the HBM figure is an "
+                    "upper bound on the traffic, not the traffic"}
 
 
 if __name__ == "__main__":

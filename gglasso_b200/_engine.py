@@ -43,74 +43,113 @@ def require_cuda():
 
 
 def to_dev(a, dev):
-    """numpy (or torch) -> contiguous FP64 device tensor (copy)."""
+    """numpy (or torch) -> contiguous FP64 device tensor (copy).
+
+    Large host arrays go through pinned staging buffers filled by several host threads at once (numpy's copy releases
+    the GIL; a single thread moves ~5-8 GB/s, far below the PCIe link), each thread feeding its own CUDA stream."""
     if isinstance(a, torch.Tensor):
         return a.to(device=dev, dtype=torch.float64, copy=True).contiguous()
     a = np.ascontiguousarray(a, dtype=np.float64)
     if a.nbytes < (8 << 20):
         return torch.from_numpy(a).to(dev, non_blocking=False)
-    # large inputs: host memcpy into two pinned staging buffers overlapped with async H2D of the previous chunk
-    bufs, evs = _staging()
-    ce = bufs[0].numel()
+    dev = torch.device(dev)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    with _H2D_LOCK:
+        return _to_dev_staged(a, dev)
+
+
+def _to_dev_staged(a, dev):
     out = torch.empty(a.shape, dtype=torch.float64, device=dev)
     src = torch.from_numpy(a).view(-1)
     dst = out.view(-1)
     n = src.numel()
-    for i, lo in enumerate(range(0, n, ce)):
-        hi = min(n, lo + ce)
-        b = bufs[i & 1]
-        evs[i & 1].synchronize()                       # previous H2D out of this buffer has finished
-        b[:hi - lo].copy_(src[lo:hi])
-        dst[lo:hi].copy_(b[:hi - lo], non_blocking=True)
-        evs[i & 1].record()
-    torch.cuda.current_stream().synchronize()
+    lanes = _h2d_lanes(dev)
+    nl = len(lanes)
+    per = (n + nl - 1) // nl
+    main = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(main)                                 # `out` was allocated on the main stream
+
+    def work(w):
+        lo0, hi0 = w * per, min(n, (w + 1) * per)
+        bufs, evs, stream = lanes[w]
+        ce = bufs[0].numel()
+        torch.cuda.set_device(dev)
+        stream.wait_event(start)
+        with torch.cuda.stream(stream):
+            for i, lo in enumerate(range(lo0, hi0, ce)):
+                hi = min(hi0, lo + ce)
+                evs[i & 1].synchronize()               # previous H2D out of this buffer has finished
+                bufs[i & 1][:hi - lo].copy_(src[lo:hi])
+                dst[lo:hi].copy_(bufs[i & 1][:hi - lo], non_blocking=True)
+                evs[i & 1].record(stream)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return done
+
+    for done in _pool().map(work, range(nl)):
+        main.wait_event(done)
     return out
 
 
 _STAGE = {}
+_H2D_LOCK = __import__("threading").Lock()
+_H2D_THREADS = max(1, _env_int("GG_H2D_THREADS", 4))
 
 
-def _staging(chunk_bytes=32 << 20):
-    if "bufs" not in _STAGE:
-        _STAGE["bufs"] = [torch.empty(chunk_bytes // 8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        _STAGE["evs"] = [torch.cuda.Event(), torch.cuda.Event()]
-        for ev in _STAGE["evs"]:
-            ev.record()
-    return _STAGE["bufs"], _STAGE["evs"]
+def _pool():
+    if "pool" not in _STAGE:
+        from concurrent.futures import ThreadPoolExecutor
+        _STAGE["pool"] = ThreadPoolExecutor(max_workers=_H2D_THREADS, thread_name_prefix="gg_h2d")
+    return _STAGE["pool"]
+
+
+def _h2d_lanes(dev, chunk_bytes=16 << 20):
+    """per device: one lane per copy thread = (two pinned staging buffers, their events, a CUDA stream)"""
+    key = ("lanes", dev.index)
+    if key not in _STAGE:
+        lanes = []
+        for _ in range(_H2D_THREADS):
+            bufs = [torch.empty(chunk_bytes // 8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            evs = [torch.cuda.Event(), torch.cuda.Event()]
+            lanes.append((bufs, evs, torch.cuda.Stream(device=dev)))
+        _STAGE[key] = lanes
+    return _STAGE[key]
 
 
 def warmup():
     """one-time process initialisation (library load, pinned staging buffers); optional."""
     _lib.load()
-    require_cuda()
-    _staging()
+    dev = require_cuda()
+    _h2d_lanes(dev)
+    _pool()
 
 
-def to_host(t, chunk_bytes=32 << 20):
-    """device tensor -> fresh numpy array through two pinned staging buffers (chunked, copy of chunk i+1
-    overlaps the host-side memcpy of chunk i).  Pageable cudaMemcpy reaches only ~2 GB/s on the GPU boxes."""
+def to_host(t):
+    """device tensor -> fresh numpy array.  The array lives in page-locked memory from torch's caching host allocator
+    (returned to the cache when the caller drops the array), so the device->host DMA writes the result directly --
+    no staging buffer and no host-side memcpy; repeated calls reuse the pinned blocks."""
     t = t.contiguous()
-    n = t.numel()
-    out = np.empty(tuple(t.shape), dtype=np.float64)
-    if n * 8 <= (1 << 20):
-        out[...] = t.cpu().numpy()
-        return out
-    bufs, evs = _staging(chunk_bytes)
-    ce = bufs[0].numel()
-    src = t.view(-1)
-    dst = torch.from_numpy(out).view(-1)
-    nchunks = (n + ce - 1) // ce
-    for i in range(nchunks + 1):
-        if i < nchunks:
-            lo, hi = i * ce, min(n, (i + 1) * ce)
-            bufs[i & 1][:hi - lo].copy_(src[lo:hi], non_blocking=True)
-            evs[i & 1].record()
-        if i >= 1:
-            j = i - 1
-            lo, hi = j * ce, min(n, (j + 1) * ce)
-            evs[j & 1].synchronize()
-            dst[lo:hi].copy_(bufs[j & 1][:hi - lo])
-    return out
+    if t.numel() * 8 <= (1 << 20):
+        return t.cpu().numpy()
+    host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
+
+
+def to_host_many(tensors):
+    """several device tensors -> numpy arrays with all copies in flight before one synchronisation"""
+    hosts = []
+    for t in tensors:
+        t = t.contiguous()
+        h = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        hosts.append(h)
+    if tensors:
+        torch.cuda.current_stream(tensors[0].device).synchronize()
+    return [h.numpy() for h in hosts]
 
 
 _DEBUG_KEEP_INPUT = bool(int(os.environ.get("GG_DEBUG_KEEP_INPUT", "0")))
@@ -329,7 +368,7 @@ class AdmmState:
         else:
             side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            out = [to_host(t) for t in tensors]
+            out = to_host_many(tensors)
         return out
 
     def min_eig(self, A):

@@ -27,6 +27,7 @@ SIGNATURES = {
     "gg_eigh": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _sz, _i, _i, _d, _i, _d, ctypes.POINTER(_i), _vp, _vp]),
     "gg_sytrd_profile": (_i, [_vp, _vp, _i, _i, _vp, _sz, _i, _vp]),
     "gg_sytrd_write_depth": (_i, []),
+    "gg_sytrd_phase_clock": (_i, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "gg_recon": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gg_sgl_nparts": (_i, [_i, _i]),
     "gg_prox_sgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _i, _vp, _vp, _vp]),

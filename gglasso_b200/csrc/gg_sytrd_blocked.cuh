@@ -8,16 +8,20 @@
 //                                CLUSTER of CS CTAs (CS in {4,6,8,16}); the upper triangle of the trailing matrix A0
 //                                (as of the panel start) is dealt to the CTAs in blocks of 8 rows, block-cyclically.
 //                                As much of a CTA's strip as fits is kept RESIDENT in shared memory for the whole
-//                                panel, the rest is streamed (ld.global.cg) once per column.  Per column j:
+//                                panel, the rest is streamed once per column -- with an L2 evict_last hint for as
+//                                much of it as the L2 can hold and evict_first for the remainder, so that the
+//                                cyclic sweep does not thrash the cache.  Per column j (v_j known to every CTA):
 //                                  y   = A0 v_j          every CTA multiplies its strip, both ways (row sums and
 //                                                        mirrored column sums: one pass over the half matrix)
-//                                  X1  reduce-scatter of the partial y over distributed shared memory
-//                                  y  -= V (W^T v) + W (V^T v)   (pending panel updates, dlatrd), p = tau y
-//                                  X2  all-gather of the partial p.v, broadcast of the pivot row of V, W
-//                                  w_j = p - (tau/2)(p.v) v ; next row a' = A0[j+1,:] - V W[j+1,:]^T - W V[j+1,:]^T
-//                                  X3  all-gather of a' and of its partial norms -> every CTA forms v_{j+1}
-//                                three cluster barriers per column instead of two kernel launches; nothing but the
-//                                Householder vectors and w_j is written to global memory.
+//                                  X1  reduce-scatter of the partial y over distributed shared memory (+ partial
+//                                      W^T v, V^T v, and the pivot row of V, W from its owner)
+//                                  y  -= V (W^T v) + W (V^T v)   (pending panel updates, dlatrd), p = tau y,
+//                                  z   = (A0[j+1,:] - V W[j+1,:]^T - W V[j+1,:]^T) - p        on the own entries
+//                                  X2  all-gather of z, of the partial p.v and of p at the pivot row
+//                                  every CTA: alpha = (tau/2) p.v, next row a' = z + (2 alpha - p_piv) v_j, its norm,
+//                                  v_{j+1}; own rows: w_j = p - alpha v_j
+//                                two cluster barriers per column instead of two kernel launches; no global memory
+//                                traffic inside the column loop except the streamed part of the strip.
 //   update  sytrd_syr2k_kernel   A[T,T] -= V W^T + W V^T on the upper triangle of the remaining block, FP64 tensor
 //                                cores (DMMA m8n8k4), one CTA per 64x64 tile, K = 2 PB.
 //
@@ -27,7 +31,8 @@
 namespace cg = cooperative_groups;
 
 #define PB_THREADS 256
-#define PB_WR (PB_THREADS / 128)   // row groups of the strip product: warps = PB_WR x 4 column groups
+#define PB_CG 4                        // column groups of the strip product (a warp takes every PB_CG-th 32-column chunk)
+#define PB_WR (PB_THREADS / 32 / PB_CG)  // row groups: warps = PB_WR x PB_CG
 #define PB_H 8                 // rows per ownership block
 #define PB_MAXCS 16
 #define PB_NMAX 2048           // largest matrix size on this path (column accumulators live in registers)
@@ -40,38 +45,43 @@ struct PanelGeom {
     int res_doubles;           // shared-memory doubles available for the resident part of the strip
 };
 
-// shared-memory carve-up (in doubles) -- must match sytrd_panel_smem_doubles() on the host
+// shared-memory carve-up (in doubles) -- must match sytrd_panel_fixed_doubles() on the host
 template <int NB>
 struct PanelSmem {
-    double *vfull, *vnext, *ycol, *rowp, *yin, *gin, *gbuf, *gtot, *bc2, *bc3, *piv, *Vs, *Ws, *pown, *red, *strip;
-    int* boff;
+    double *vfull, *vnext, *ycol, *rowp, *yin, *gin, *gbuf, *gtot, *bc2, *piv, *Vs, *Ws, *pown, *vown, *red, *arows, *sc, *strip;
+    int *boff, *otab, *itab;
     __device__ __forceinline__ void carve(double* base, int TP, int NO, int CS, int nqmax)
     {
         double* q = base;
-        vfull = q; q += TP;
-        vnext = q; q += TP;
-        ycol = q; q += PB_WR * TP;
-        rowp = q; q += 4 * NO;
-        yin = q; q += CS * NO;
-        gin = q; q += CS * 2 * NB;
+        vfull = q; q += TP;           // v_j, every entry
+        vnext = q; q += TP;           // z of the next pivot row, every entry (written by all CTAs of the cluster)
+        ycol = q; q += PB_WR * TP;    // column sums of the strip product, one slice per warp row group
+        rowp = q; q += PB_CG * NO;    // row sums, one slice per warp column group
+        yin = q; q += CS * NO;        // partial y of the own rows from every CTA
+        gin = q; q += CS * 2 * NB;    // partial [W^T v ; V^T v] from every CTA
         gbuf = q; q += 2 * NB;
         gtot = q; q += 2 * NB;
-        bc2 = q; q += PB_MAXCS;
-        bc3 = q; q += PB_MAXCS;
-        piv = q; q += 2 * NB + 2;
-        Vs = q; q += NO * (NB + 1);
+        bc2 = q; q += PB_MAXCS;       // partial p.v from every CTA
+        piv = q; q += 2 * (2 * NB + 2);   // pivot row, two buffers (column parity): [0] p, [1..NB] V, [NB+1..2NB] W
+        Vs = q; q += NO * (NB + 1);   // own rows of the panel's V and W
         Ws = q; q += NO * (NB + 1);
         pown = q; q += NO;
+        vown = q; q += NO;            // v_j on the own rows
         red = q; q += 64;
+        arows = q; q += NB * NO;      // own entries of the panel's pivot rows of A0
+        sc = q; q += 4 * NB;          // d, e, tau of the panel and the diagonal entries of the pivot rows
         boff = (int*)q; q += (nqmax + 1) / 2 + 1;
+        otab = (int*)q; q += TP / 2;  // entry i -> (owner << 16) | slot
+        itab = (int*)q; q += (NO + 1) / 2 + 1;   // own slot -> entry
         strip = q;
     }
 };
 
 static inline size_t sytrd_panel_fixed_doubles(int NB, int TP, int NO, int CS, int nqmax)
 {
-    return (size_t)(2 + PB_WR) * TP + 4 * NO + (size_t)CS * NO + (size_t)CS * 2 * NB + 4 * NB + 2 * PB_MAXCS + 2 * NB + 2 +
-           (size_t)2 * NO * (NB + 1) + NO + 64 + (nqmax + 1) / 2 + 1;
+    return (size_t)(2 + PB_WR) * TP + PB_CG * NO + (size_t)CS * NO + (size_t)CS * 2 * NB + 4 * NB + PB_MAXCS + 2 * (2 * NB + 2) +
+           (size_t)2 * NO * (NB + 1) + 2 * NO + 64 + (size_t)NB * NO + 4 * NB + (nqmax + 1) / 2 + 1 + TP / 2 +
+           (NO + 1) / 2 + 1;
 }
 
 // 8 per-lane partial sums -> lane l holds the warp total of element (l >> 2)
@@ -106,12 +116,18 @@ __device__ __forceinline__ double pb_reduce8(double (&r)[8], int lane)
 // The kernel is bound by instruction issue, so the chunks strictly between the diagonal chunk and the ragged last
 // chunk of a full block run without any predicate (two chunks per trip: 16 independent loads in flight per lane).
 template <bool RES>
-__device__ __forceinline__ double pb_ld(const double* p) { return RES ? *p : __ldcg(p); }
+__device__ __forceinline__ double pb_ld(const double* p, unsigned long long pol)
+{
+    if (RES) return *p;
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
 
 template <bool RES>
 __device__ __forceinline__ void pb_block_matvec(const double* __restrict__ src, int pitch, int r0, int t, int g, int lane,
                                                 const double* __restrict__ vfull, double* __restrict__ ycw,
-                                                double (&racc)[8])
+                                                double (&racc)[8], unsigned long long pol)
 {
     const int ch0 = r0 >> 5;                         // chunk holding the diagonal of this block
     const int chl = (t - 1) >> 5;                    // last chunk with valid columns
@@ -120,7 +136,7 @@ __device__ __forceinline__ void pb_block_matvec(const double* __restrict__ src, 
     double vr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) vr[i] = vfull[r0 + i];
-    int ch = g + 4 * ((ch0 - g + 3) >> 2);           // first chunk of this warp at or right of the diagonal chunk
+    int ch = g + PB_CG * ((ch0 - g + PB_CG - 1) / PB_CG);   // first chunk of this warp at or right of the diagonal chunk
     // masked trip: diagonal chunk, ragged last chunk, or a block with fewer than 8 rows
     auto masked = [&](int chm) {
         const int cc = 32 * chm + lane;
@@ -129,7 +145,7 @@ __device__ __forceinline__ void pb_block_matvec(const double* __restrict__ src, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool ok = on && (i < rows) && (cc >= r0 + i);
-            a[i] = ok ? pb_ld<RES>(src + (size_t)i * pitch + (cc - r0)) : 0.0;
+            a[i] = ok ? pb_ld<RES>(src + (size_t)i * pitch + (cc - r0), pol) : 0.0;
         }
         const double vcc = on ? vfull[cc] : 0.0;
         double cs = 0.0;
@@ -141,20 +157,20 @@ __device__ __forceinline__ void pb_block_matvec(const double* __restrict__ src, 
         if (on) ycw[cc] += cs;
     };
     if (rows < PB_H) {
-        for (; ch <= chl; ch += 4) masked(ch);
+        for (; ch <= chl; ch += PB_CG) masked(ch);
         return;
     }
-    if (ch == ch0) { masked(ch); ch += 4; }
+    if (ch == ch0) { masked(ch); ch += PB_CG; }
     const int chi = (ragged ? chl - 1 : chl);        // last chunk that may take the unmasked path
     const double* p = src + (32 * ch + lane - r0);
-    for (; ch + 4 <= chi; ch += 8, p += 256) {
+    for (; ch + PB_CG <= chi; ch += 2 * PB_CG, p += 64 * PB_CG) {
         double a[8], b[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = pb_ld<RES>(p + (size_t)i * pitch);
+        for (int i = 0; i < 8; ++i) a[i] = pb_ld<RES>(p + (size_t)i * pitch, pol);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = pb_ld<RES>(p + (size_t)i * pitch + 128);
+        for (int i = 0; i < 8; ++i) b[i] = pb_ld<RES>(p + (size_t)i * pitch + 32 * PB_CG, pol);
         const int cc = 32 * ch + lane;
-        const double va = vfull[cc], vb = vfull[cc + 128];
+        const double va = vfull[cc], vb = vfull[cc + 32 * PB_CG];
         double ca = 0.0, cb = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -167,12 +183,12 @@ __device__ __forceinline__ void pb_block_matvec(const double* __restrict__ src, 
             cb = fma(b[i], vr[i], cb);
         }
         ycw[cc] += ca;
-        ycw[cc + 128] += cb;
+        ycw[cc + 32 * PB_CG] += cb;
     }
     if (ch <= chi) {
         double a[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = pb_ld<RES>(p + (size_t)i * pitch);
+        for (int i = 0; i < 8; ++i) a[i] = pb_ld<RES>(p + (size_t)i * pitch, pol);
         const int cc = 32 * ch + lane;
         const double va = vfull[cc];
         double ca = 0.0;
@@ -182,15 +198,34 @@ __device__ __forceinline__ void pb_block_matvec(const double* __restrict__ src, 
             ca = fma(a[i], vr[i], ca);
         }
         ycw[cc] += ca;
-        ch += 4;
+        ch += PB_CG;
     }
     if (ch <= chl) masked(ch);                       // ragged last chunk
 }
 
+// phase clock of the panel kernel (diagnostics, GG_TR_TIMING=1): nanoseconds summed over all columns by thread 0 of
+// the first CTA; [0] X3 exchange  [1] Householder + g partials  [2] strip product  [3] X1 exchange  [4] correction
+// [5] X2 exchange  [6] w and next row  [7] panel prologue (strip load)  [8] columns
+__device__ unsigned long long pb_phase_ns[16];
+__device__ __forceinline__ unsigned long long pb_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PB_STAMP(slot)                                                   \
+    do {                                                                 \
+        if (clock_on) {                                                  \
+            const unsigned long long now_ = pb_now();                    \
+            acc_ns[slot] += now_ - last_ns;                              \
+            last_ns = now_;                                              \
+        }                                                                \
+    } while (0)
+
 template <int NB>
 __global__ void __launch_bounds__(PB_THREADS, 1)
 sytrd_panel_kernel(const double* __restrict__ A, int n, int p0, int nbk, TrWs ws, double* __restrict__ Wp,
-                   const int* __restrict__ skip, int res_doubles)
+                   const int* __restrict__ skip, int res_doubles, int l2_doubles, int timing)
 {
     extern __shared__ __align__(16) double pbsm[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -199,6 +234,8 @@ sytrd_panel_kernel(const double* __restrict__ A, int n, int p0, int nbk, TrWs ws
     const int m = blockIdx.x / CS;
     if (skip && skip[m]) return;                    // uniform over the cluster: no barrier is left waiting
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool clock_on = timing && blockIdx.x == 0 && tid == 0;
+    unsigned long long acc_ns[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, last_ns = clock_on ? pb_now() : 0;
     const int base = p0 + 1, t = n - base;
     const int TP = (t + 31) & ~31;
     const int nblk = (t + PB_H - 1) / PB_H;
@@ -213,18 +250,25 @@ sytrd_panel_kernel(const double* __restrict__ A, int n, int p0, int nbk, TrWs ws
     double* Vh = ws.Vh + (size_t)m * n * n;
     double* Wm = Wp + (size_t)m * NB * n;
     const int LDV = NB + 1;
-    // local index of own slot s
-    auto idx_of = [&](int s) { return PB_H * (c + CS * (s >> 3)) + (s & 7); };
+    unsigned long long pol_last, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 
-    // ---- resident part of the strip: blocks in order until the budget is used up ---------------------------------
+    // ---- tables; resident / L2-pinned split of the strip: blocks in order until each budget is used up ------------
+    for (int i = tid; i < TP; i += PB_THREADS) {
+        const int B = i >> 3;
+        S.otab[i] = ((B % CS) << 16) | (((B / CS) << 3) | (i & 7));
+    }
+    for (int sl = tid; sl < nown; sl += PB_THREADS) S.itab[sl] = PB_H * (c + CS * (sl >> 3)) + (sl & 7);
     if (tid == 0) {
-        int used = 0;
+        int used = 0, l2used = 0;
         for (int q = 0; q < nq; ++q) {
             const int r0 = PB_H * (c + CS * q);
             const int pitch = (t - r0 + 1) & ~1;
             const int need = PB_H * pitch;
             if (used + need <= res_doubles) { S.boff[q] = used; used += need; }
-            else S.boff[q] = -1;
+            else if (l2used + need <= l2_doubles) { S.boff[q] = -1; l2used += need; }      // streamed, kept in L2
+            else S.boff[q] = -2;                                                           // streamed, evict first
         }
     }
     __syncthreads();
@@ -233,105 +277,127 @@ sytrd_panel_kernel(const double* __restrict__ A, int n, int p0, int nbk, TrWs ws
         if (off < 0) continue;
         const int r0 = PB_H * (c + CS * q);
         const int len = t - r0, pitch = (len + 1) & ~1;
-        for (int e = tid; e < PB_H * pitch; e += PB_THREADS) {
-            const int i = e / pitch, cc = e - i * pitch;
-            double v = 0.0;
-            if (r0 + i < t && cc < len && cc >= i) v = __ldcg(A0 + (size_t)(r0 + i) * n + r0 + cc);
-            S.strip[off + e] = v;
-        }
-    }
-    // ---- prologue: row p0 right of the diagonal is the first row to eliminate --------------------------------------
-    double arow[2];                                 // own entries of the current pivot row (slots tid, tid + 256)
-    double part = 0.0;
+        for (int cc = tid; cc < pitch; cc += 2 * PB_THREADS) {
+            double v[2][PB_H];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int s = tid + PB_THREADS * u;
-        arow[u] = 0.0;
-        if (s < nown) {
-            const int i = idx_of(s);
-            if (i < t) arow[u] = Am[(size_t)p0 * n + base + i];
-            if (i >= 1) part += arow[u] * arow[u];
-        }
-    }
-    if (c == 0 && tid == 0) ws.d[(size_t)m * n + p0] = Am[(size_t)p0 * n + p0];
-    cluster.sync();                                 // every CTA of the cluster is running: remote shared memory is valid
-
-    for (int jj = 0; jj < nbk; ++jj) {
-        const int j = p0 + jj;
-        // ================= X3: all-gather of the unscaled row a' and of its partial norms ========================
-        {
-            const double xn_c = tr_block_allsum(part, S.red);
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int s = tid + PB_THREADS * u;
-                if (s < nown) {
-                    const int i = idx_of(s);
-                    for (int r = 0; r < CS; ++r) cluster.map_shared_rank(S.vnext, r)[i] = arow[u];
+                for (int i = 0; i < PB_H; ++i) {
+                    const int cu = cc + u * PB_THREADS;
+                    v[u][i] = (r0 + i < t && cu < len && cu >= i) ? __ldcg(A0 + (size_t)(r0 + i) * n + r0 + cu) : 0.0;
                 }
-            }
-            if (tid < CS) cluster.map_shared_rank(S.bc3, tid)[c] = xn_c;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int i = 0; i < PB_H; ++i)
+                    if (cc + u * PB_THREADS < pitch) S.strip[off + i * pitch + cc + u * PB_THREADS] = v[u][i];
         }
-        cluster.sync();
-        // ================= G: Householder vector v_j (every CTA, identically) ====================================
-        double tau_j;
-        {
-            double xn2 = 0.0;
-            for (int r = 0; r < CS; ++r) xn2 += S.bc3[r];
-            const double alpha = S.vnext[jj];
-            double beta = alpha, scale = 0.0;
-            tau_j = 0.0;
-            if (xn2 > 0.0) {
-                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-                tau_j = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+    }
+    // own entries of the pivot rows of A0 used inside the panel (row local k is eliminated at column k + 1) and their
+    // diagonal entries: staged now, so that no global load is outstanding at any cluster barrier of the column loop
+    for (int sl = tid; sl < nown; sl += PB_THREADS) {
+        const int i = S.itab[sl];
+        for (int k0 = 0; k0 < nbk - 1; k0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                v[u] = (k < nbk - 1 && i > k && i < t) ? __ldcg(A0 + (size_t)k * n + i) : 0.0;
             }
-            for (int i = tid; i < TP; i += PB_THREADS) {
-                double v = 0.0;
-                if (i == jj) v = 1.0;
-                else if (i > jj && i < t) v = S.vnext[i] * scale;
-                S.vfull[i] = v;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < nbk - 1) S.arows[(k0 + u) * NO + sl] = v[u];
+        }
+    }
+    if (tid < nbk - 1) S.sc[3 * NB + tid] = __ldcg(A0 + (size_t)tid * n + tid);
+    if (tid == 0) S.sc[0] = Am[(size_t)p0 * n + p0];               // d[p0]
+    // the first row to eliminate, row p0 right of the diagonal: every CTA reads all of it (z of "column -1")
+    for (int i = tid; i < TP; i += PB_THREADS) {
+        S.vnext[i] = (i < t) ? Am[(size_t)p0 * n + base + i] : 0.0;
+        S.vfull[i] = 0.0;
+    }
+    cluster.sync();                                 // every CTA of the cluster is running: remote shared memory is valid
+    PB_STAMP(7);
+
+    double tau_prev = 0.0;                          // tau of column jj - 1
+    for (int jj = 0; jj <= nbk; ++jj) {
+        // ================= G: finish column jj-1 (alpha, w), form the next row a' and v_jj ==========================
+        // the pivot-row buffer alternates with the column parity: the owner of the next pivot row may already be
+        // writing this column's values (X1) while a slower CTA still reads the previous ones here
+        const double* pivp = S.piv + ((jj + 1) & 1) * (2 * NB + 2);     // written during column jj-1
+        double* pivc = S.piv + (jj & 1) * (2 * NB + 2);                 // written during this column
+        double al = 0.0, beta2 = 0.0;
+        if (jj > 0) {
+            double dot = 0.0;
+            for (int r = 0; r < CS; ++r) dot += S.bc2[r];
+            al = 0.5 * tau_prev * dot;
+            beta2 = 2.0 * al - pivp[0];
+            for (int sl = tid; sl < nown; sl += PB_THREADS) {
+                const int i = S.itab[sl];
+                S.Ws[sl * LDV + jj - 1] = (i >= jj - 1 && i < t) ? S.pown[sl] - al * S.vfull[i] : 0.0;      // w_{jj-1}
             }
-            if (c == 0 && tid == 0) {
-                ws.tau[(size_t)m * n + j] = tau_j;
-                ws.e[(size_t)m * n + j] = beta;
+        }
+        if (jj == nbk) break;
+        double areg[PB_NMAX / PB_THREADS];
+        double part = 0.0;
+#pragma unroll
+        for (int u = 0; u < PB_NMAX / PB_THREADS; ++u) {
+            const int i = tid + PB_THREADS * u;
+            areg[u] = 0.0;
+            if (i < t && i >= jj) {
+                areg[u] = fma(beta2, S.vfull[i], S.vnext[i]);                      // a' = z + (2 alpha - p_piv) v
+                if (i > jj) part = fma(areg[u], areg[u], part);
             }
+        }
+        const double alpha = fma(beta2, S.vfull[jj], S.vnext[jj]);
+        const double xn2 = tr_block_allsum(part, S.red);                           // (barrier: old v no longer needed)
+        double beta = alpha, scale = 0.0, tau_j = 0.0;
+        if (xn2 > 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+            tau_j = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+#pragma unroll
+        for (int u = 0; u < PB_NMAX / PB_THREADS; ++u) {
+            const int i = tid + PB_THREADS * u;
+            if (i < TP) S.vfull[i] = (i == jj) ? 1.0 : ((i > jj && i < t) ? areg[u] * scale : 0.0);
+        }
+        if (tid == 0) {
+            S.sc[2 * NB + jj] = tau_j;
+            S.sc[NB + jj] = beta;
         }
         __syncthreads();
-        for (int s = tid; s < nown; s += PB_THREADS) {
-            const int i = idx_of(s);
+        for (int sl = tid; sl < nown; sl += PB_THREADS) {
+            const int i = S.itab[sl];
             const double v = (i < t) ? S.vfull[i] : 0.0;
-            S.Vs[s * LDV + jj] = v;
-            if (i >= jj && i < t) Vh[(size_t)j * n + base + i] = v;
+            S.Vs[sl * LDV + jj] = v;
+            S.vown[sl] = v;
         }
-        // prefetch the own entries of the next pivot row of A0 (row local jj) and its diagonal
-        double anext[2] = {0.0, 0.0}, adiag = 0.0;
-        if (jj + 1 < nbk) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int s = tid + PB_THREADS * u;
-                if (s < nown) {
-                    const int i = idx_of(s);
-                    if (i > jj && i < t) anext[u] = __ldcg(A0 + (size_t)jj * n + i);
-                }
-            }
-            if (tid == 0) adiag = __ldcg(A0 + (size_t)jj * n + jj);
-        }
-        // partial g = [W^T v ; V^T v] over the own rows (columns k < jj): warp w takes k = w, w + 8, ...
-        for (int k = warp; k < 2 * jj; k += PB_THREADS / 32) {
+        __syncthreads();
+        // partial g = [W^T v ; V^T v] over the own rows (columns k < jj): eight lanes per column, each over every
+        // eighth own row, combined with three shuffles
+        for (int k = tid >> 3; k < 2 * jj; k += PB_THREADS / 8) {
             const double* P = (k < jj) ? (S.Ws + k) : (S.Vs + (k - jj));
-            double acc = 0.0;
-            for (int s = lane; s < nown; s += 32) {
-                const int i = idx_of(s);
-                acc = fma(P[s * LDV], (i < t) ? S.vfull[i] : 0.0, acc);
+            double a0 = 0.0, a1 = 0.0;
+            int sl = tid & 7;
+            for (; sl + 8 < nown; sl += 16) {
+                a0 = fma(P[sl * LDV], S.vown[sl], a0);
+                a1 = fma(P[(sl + 8) * LDV], S.vown[sl + 8], a1);
             }
-            acc = tr_warp_allsum(acc);
-            if (lane == 0) S.gbuf[k] = acc;           // gbuf[0..jj) = W^T v, gbuf[jj..2jj) = V^T v
+            if (sl < nown) a0 = fma(P[sl * LDV], S.vown[sl], a0);
+            double acc = a0 + a1;
+            const unsigned gm = 0xffu << (lane & 24);          // the eight lanes that share this column (same trip count)
+            acc += __shfl_xor_sync(gm, acc, 1);
+            acc += __shfl_xor_sync(gm, acc, 2);
+            acc += __shfl_xor_sync(gm, acc, 4);
+            if ((tid & 7) == 0) S.gbuf[k] = acc;      // gbuf[0..jj) = W^T v, gbuf[jj..2jj) = V^T v
         }
+        PB_STAMP(1);
         // ================= A: y = A0 v over the strip ==============================================================
         {
-            const int wr = warp >> 2, g = warp & 3;
+            const int wr = warp / PB_CG, g = warp % PB_CG;
             double* ycw = S.ycol + wr * TP;
-            for (int cc = 32 * g + lane; cc < TP; cc += 128) ycw[cc] = 0.0;      // this warp's columns of its row group
+            for (int cc = 32 * g + lane; cc < TP; cc += 32 * PB_CG) ycw[cc] = 0.0;      // this warp's columns of its row group
             __syncwarp();
             for (int q = wr; q < nq; q += PB_WR) {
                 const int r0 = PB_H * (c + CS * q);
@@ -341,28 +407,47 @@ sytrd_panel_kernel(const double* __restrict__ A, int n, int p0, int nbk, TrWs ws
                 if (r0 + PB_H > jj) {                 // rows above the current column carry v = 0
                     const int off = S.boff[q];
                     if (off >= 0)
-                        pb_block_matvec<true>(S.strip + off, (t - r0 + 1) & ~1, r0, t, g, lane, S.vfull, ycw, racc);
+                        pb_block_matvec<true>(S.strip + off, (t - r0 + 1) & ~1, r0, t, g, lane, S.vfull, ycw, racc, 0ull);
                     else
-                        pb_block_matvec<false>(A0 + (size_t)r0 * n + r0, n, r0, t, g, lane, S.vfull, ycw, racc);
+                        pb_block_matvec<false>(A0 + (size_t)r0 * n + r0, n, r0, t, g, lane, S.vfull, ycw, racc,
+                                               off == -1 ? pol_last : pol_first);
                 }
                 const double tot = pb_reduce8(racc, lane);
                 if ((lane & 3) == 0) S.rowp[g * NO + q * PB_H + (lane >> 2)] = tot;
             }
         }
         __syncthreads();
-        // ================= X1: reduce-scatter of the partial y, all-gather of the partial g =======================
-        for (int i = tid; i < t; i += PB_THREADS) {
-            const int B = i >> 3, owner = B % CS, s = ((B / CS) << 3) | (i & 7);
-            double v = 0.0;
+        PB_STAMP(2);
+        // ================= X1: reduce-scatter of the partial y, all-gather of the partial g, pivot row of V, W =====
+        for (int i = 2 * tid; i < t; i += 2 * PB_THREADS) {        // pairs (i, i+1): same 8-row block, same owner
+            const int ot = S.otab[i], owner = ot >> 16, sl = ot & 0xffff;
+            double2 v = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int w = 0; w < PB_WR; ++w) v += S.ycol[w * TP + i];
-            if (owner == c) v += (S.rowp[s] + S.rowp[NO + s]) + (S.rowp[2 * NO + s] + S.rowp[3 * NO + s]);
-            cluster.map_shared_rank(S.yin, owner)[c * NO + s] = v;
+            for (int w = 0; w < PB_WR; ++w) {
+                const double2 yc = *reinterpret_cast<const double2*>(S.ycol + w * TP + i);
+                v.x += yc.x; v.y += yc.y;
+            }
+            if (owner == c) {
+#pragma unroll
+                for (int w = 0; w < PB_CG; ++w) {
+                    const double2 rp = *reinterpret_cast<const double2*>(S.rowp + w * NO + sl);
+                    v.x += rp.x; v.y += rp.y;
+                }
+            }
+            *reinterpret_cast<double2*>(cluster.map_shared_rank(S.yin, owner) + c * NO + sl) = v;
         }
         if (tid < 2 * jj)
             for (int r = 0; r < CS; ++r) cluster.map_shared_rank(S.gin, r)[c * 2 * NB + tid] = S.gbuf[tid];
+        const int otp = S.otab[jj], powner = otp >> 16, psl = otp & 0xffff;       // next pivot row: local row jj
+        if (powner == c && tid >= 1 && tid <= 2 * NB) {
+            double v;
+            if (tid <= NB) v = (tid - 1 <= jj) ? S.Vs[psl * LDV + tid - 1] : 0.0;
+            else v = (tid - 1 - NB < jj) ? S.Ws[psl * LDV + tid - 1 - NB] : 0.0;
+            for (int r = 0; r < CS; ++r) cluster.map_shared_rank(pivc, r)[tid] = v;
+        }
         cluster.sync();
-        // ================= C: y on the own rows, panel correction, p = tau y, partial p.v ==========================
+        PB_STAMP(3);
+        // ================= C: y on the own rows, panel correction, p = tau y, z of the next pivot row ===============
         if (tid < 2 * jj) {
             double gsum = 0.0;
             for (int r = 0; r < CS; ++r) gsum += S.gin[r * 2 * NB + tid];
@@ -370,80 +455,70 @@ sytrd_panel_kernel(const double* __restrict__ A, int n, int p0, int nbk, TrWs ws
         }
         __syncthreads();
         double dp = 0.0;
-        for (int s = tid; s < nown; s += PB_THREADS) {
-            const int i = idx_of(s);
+        for (int sl = tid; sl < nown; sl += PB_THREADS) {
+            const int i = S.itab[sl];
             double y = 0.0;
-            for (int r = 0; r < CS; ++r) y += S.yin[r * NO + s];
-            double c0 = 0.0, c1 = 0.0;
+            for (int r = 0; r < CS; ++r) y += S.yin[r * NO + sl];
+            double c0 = 0.0, c1 = 0.0, b0 = 0.0, b1 = 0.0;
             for (int k = 0; k < jj; ++k) {
-                c0 = fma(S.Vs[s * LDV + k], S.gtot[k], c0);            // V (W^T v)
-                c1 = fma(S.Ws[s * LDV + k], S.gtot[jj + k], c1);       // W (V^T v)
+                const double vk = S.Vs[sl * LDV + k], wk = S.Ws[sl * LDV + k];
+                c0 = fma(vk, S.gtot[k], c0);                      // V (W^T v)
+                c1 = fma(wk, S.gtot[jj + k], c1);                 // W (V^T v)
+                b0 = fma(pivc[1 + k], wk, b0);                    // V[piv][k] W[i][k]
+                b1 = fma(pivc[1 + NB + k], vk, b1);               // W[piv][k] V[i][k]
             }
             y -= c0 + c1;
-            double pv = 0.0;
+            double pv = 0.0, z = 0.0;
             if (i >= jj && i < t) {
                 pv = tau_j * y;
                 dp = fma(pv, S.vfull[i], dp);
             }
-            S.pown[s] = pv;
+            S.pown[sl] = pv;
+            if (jj + 1 < nbk && i > jj && i < t) z = (S.arows[jj * NO + sl] - (b0 + b1)) - pv;
+            if (jj + 1 < nbk)
+                for (int r = 0; r < CS; ++r) cluster.map_shared_rank(S.vnext, r)[i] = z;
         }
         const double dp_c = tr_block_allsum(dp, S.red);               // (barrier: pown complete)
-        // ================= X2: partial dots, pivot row (local row jj) of p, V, W ==================================
+        PB_STAMP(4);
+        // ================= X2: partial dots, p at the pivot row ======================================================
         if (tid < CS) cluster.map_shared_rank(S.bc2, tid)[c] = dp_c;
-        {
-            const int Bp = jj >> 3;
-            if (Bp % CS == c) {
-                const int sp = ((Bp / CS) << 3) | (jj & 7);
-                if (tid <= 2 * NB) {
-                    double v;
-                    if (tid == 0) v = S.pown[sp];
-                    else if (tid <= NB) v = (tid - 1 <= jj) ? S.Vs[sp * LDV + tid - 1] : 0.0;
-                    else v = (tid - 1 - NB < jj) ? S.Ws[sp * LDV + tid - 1 - NB] : 0.0;
-                    for (int r = 0; r < CS; ++r) cluster.map_shared_rank(S.piv, r)[tid] = v;
-                }
-            }
-        }
+        if (powner == c && tid < CS) cluster.map_shared_rank(pivc, tid)[0] = S.pown[psl];
         cluster.sync();
-        // ================= E: w_j, next pivot row, its diagonal and partial norm ===================================
-        {
-            double dot = 0.0;
-            for (int r = 0; r < CS; ++r) dot += S.bc2[r];
-            const double al = 0.5 * tau_j * dot;
-            const double wpiv = S.piv[0] - al;                        // w_j at the pivot row (v_j = 1 there)
-            part = 0.0;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int s = tid + PB_THREADS * u;
-                arow[u] = 0.0;
-                if (s < nown) {
-                    const int i = idx_of(s);
-                    double w = 0.0;
-                    if (i >= jj && i < t) w = S.pown[s] - al * S.vfull[i];
-                    S.Ws[s * LDV + jj] = w;
-                    if (i >= jj && i < t) Wm[(size_t)jj * n + base + i] = w;
-                    if (jj + 1 < nbk && i > jj && i < t) {
-                        double c0 = 0.0, c1 = 0.0;
-                        for (int k = 0; k < jj; ++k) {
-                            c0 = fma(S.piv[1 + k], S.Ws[s * LDV + k], c0);          // V[piv][k] W[i][k]
-                            c1 = fma(S.piv[1 + NB + k], S.Vs[s * LDV + k], c1);     // W[piv][k] V[i][k]
-                        }
-                        c0 = fma(1.0, w, c0);                                        // k = jj: V[piv][jj] = 1
-                        c1 = fma(wpiv, S.vfull[i], c1);                              //         W[piv][jj] = wpiv
-                        arow[u] = anext[u] - (c0 + c1);
-                        if (i >= jj + 2) part += arow[u] * arow[u];
-                    }
-                }
-            }
-            if (jj + 1 < nbk && c == 0 && tid == 0) {
-                double s2 = 0.0;
-                for (int k = 0; k < jj; ++k) s2 = fma(S.piv[1 + k], S.piv[1 + NB + k], s2);
-                s2 += wpiv;                                                          // V[piv][jj] W[piv][jj]
-                ws.d[(size_t)m * n + j + 1] = adiag - 2.0 * s2;
-            }
+        PB_STAMP(5);
+        tau_prev = tau_j;
+    }
+    PB_STAMP(6);
+    // ---- results of the panel: Householder vectors (rows of Vh), w vectors (for the trailing update), d, e, tau ----
+    __syncthreads();
+    for (int e = tid; e < nbk * nown; e += PB_THREADS) {
+        const int k = e / nown, sl = e - k * nown;
+        const int i = S.itab[sl];
+        if (i >= k && i < t) {
+            Vh[(size_t)(p0 + k) * n + base + i] = S.Vs[sl * LDV + k];
+            Wm[(size_t)k * n + base + i] = S.Ws[sl * LDV + k];
         }
-        __syncthreads();
+    }
+    if (c == 0 && tid < nbk) {
+        if (tid == 0) ws.d[(size_t)m * n + p0] = S.sc[0];
+        ws.e[(size_t)m * n + p0 + tid] = S.sc[NB + tid];
+        ws.tau[(size_t)m * n + p0 + tid] = S.sc[2 * NB + tid];
+    }
+    // diagonal entry of local row r (pivot of column r+1 of this panel): d = A0[r][r] - 2 sum_{k<=r} V[r][k] W[r][k],
+    // from the finished panel rows of the CTA that owns row r
+    if (tid < nbk - 1) {
+        const int r = tid, ot = S.otab[r];
+        if ((ot >> 16) == c) {
+            const int sl = ot & 0xffff;
+            double s2 = 0.0;
+            for (int k = 0; k <= r; ++k) s2 = fma(S.Vs[sl * LDV + k], S.Ws[sl * LDV + k], s2);
+            ws.d[(size_t)m * n + base + r] = S.sc[3 * NB + r] - 2.0 * s2;
+        }
     }
     cluster.sync();                                   // no CTA exits while a peer may still write into its shared memory
+    if (clock_on) {
+        PB_STAMP(8);
+        for (int q = 0; q < 9; ++q) atomicAdd(&pb_phase_ns[q], acc_ns[q]);
+    }
 }
 
 // ---- trailing update on the FP64 tensor cores --------------------------------------------------------------------
@@ -519,17 +594,29 @@ sytrd_syr2k_kernel(double* __restrict__ A, int n, int p0, int nbk, const double*
         }
         __syncthreads();
     }
-    double* C = A + (size_t)m * n * n + (size_t)g0 * n + g0;
+    // epilogue through shared memory: the read-modify-write of C runs over whole 512-byte row segments
+    double* Cs = sm;                                  // 64 x 65 (the operand buffers are free now)
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int r = i0 + (wr * 2 + a) * 8 + fr;
-        if (r >= tt) continue;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int cc = j0 + (wc * 4 + b) * 8 + 2 * fc;
-            double* dst = C + (size_t)r * n + cc;
-            if (cc < tt && cc >= r) dst[0] -= acc[a][b][0];
-            if (cc + 1 < tt && cc + 1 >= r) dst[1] -= acc[a][b][1];
+            const int r = (wr * 2 + a) * 8 + fr, cc = (wc * 4 + b) * 8 + 2 * fc;
+            Cs[r * 65 + cc] = acc[a][b][0];
+            Cs[r * 65 + cc + 1] = acc[a][b][1];
+        }
+    __syncthreads();
+    double* C = A + (size_t)m * n * n + (size_t)g0 * n + g0;
+    for (int e0 = tid; e0 < SY_T * SY_T; e0 += 4 * 256) {
+        double cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 256 * u, r = i0 + (e >> 6), cc = j0 + (e & 63);
+            cur[u] = (r < tt && cc < tt && cc >= r) ? __ldcg(C + (size_t)r * n + cc) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 256 * u, r = i0 + (e >> 6), cc = j0 + (e & 63);
+            if (r < tt && cc < tt && cc >= r) C[(size_t)r * n + cc] = cur[u] - Cs[(e >> 6) * 65 + (e & 63)];
         }
     }
 }
@@ -588,7 +675,21 @@ static int sytrd_panel_launch(const double* A, int n, int p0, int nbk, TrWs tw, 
     cfg.gridDim = dim3(M * CS); cfg.blockDim = dim3(PB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cfg.attrs = at; cfg.numAttrs = 1;
     gg_count_launch(1);
-    e = cudaLaunchKernelEx(&cfg, kern, A, n, p0, nbk, tw, Wp, skip, (int)res);
+    // L2 share of one CTA for the streamed part of its strip (evict_last): GG_TR_L2MB megabytes over all CTAs
+    const long long l2_total = (long long)sytrd_blocked_env("GG_TR_L2MB", 64) << 20;
+    const int l2_doubles = (int)(l2_total / 8 / ((long long)M * CS));
+    e = cudaLaunchKernelEx(&cfg, kern, A, n, p0, nbk, tw, Wp, skip, (int)res, l2_doubles,
+                           sytrd_blocked_env("GG_TR_TIMING", 0));
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// diagnostics: read and clear the phase clock of the panel kernels
+int gg_sytrd_phase_times(unsigned long long* out16)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out16, pb_phase_ns, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(pb_phase_ns, z, sizeof(z));
     return e == cudaSuccess ? 0 : (int)e;
 }
 

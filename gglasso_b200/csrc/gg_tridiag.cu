@@ -242,9 +242,27 @@ struct SvSmem {
     double colp[16][SV_T];                       // [ty][col] partial column sums
 };
 
+// L2 residency control of the trailing-matrix sweep.  The 2p passes of a tridiagonalisation re-read the same (shrinking)
+// set of upper triangles; while that set is larger than the L2 an LRU-like policy evicts every line before its reuse and
+// each pass comes from HBM.  The bottom-right part of every matrix (rows >= r_pin) belongs to ALL later passes: its
+// tiles are loaded / stored with an evict_last policy, the rest with evict_first, so that a fixed ~64 MB of the batch
+// stays resident from the second pass on.  hint == 0: plain ld.global.cg / st (batches that fit the L2 anyway).
+__device__ __forceinline__ double sv_ld(const double* p, int hint, unsigned long long pol)
+{
+    if (!hint) return __ldcg(p);
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void sv_st(double* p, double v, int hint, unsigned long long pol)
+{
+    if (!hint) { *p = v; return; }
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 template <bool INTERIOR>
 __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int j, int kb, int write, const TrWs& ws,
-                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm)
+                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm, int r_pin)
 {
     const int t = n - j - 1, base = j + 1, cnt = j - kb;
 #ifdef TR_TIMING
@@ -260,11 +278,17 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
     // overlap the column step.  ld.global.cg: straight from L2 -- no reuse, and no stale L1 lines across launches.
     double a[4][4];
     unsigned okm = 0xffffu;
+    const int hint = r_pin >= 0;
+    unsigned long long pol = 0;
+    if (hint) {
+        if (base + r0 >= r_pin) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    }
     if (INTERIOR) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) a[i][jj] = __ldcg(pt + (size_t)i * n + 16 * jj);
+            for (int jj = 0; jj < 4; ++jj) a[i][jj] = sv_ld(pt + (size_t)i * n + 16 * jj, hint, pol);
     } else {
         okm = 0;
 #pragma unroll
@@ -274,7 +298,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
                 const int r = rb + i, c = cb + 16 * jj;
                 const bool ok = (r < t && c < t && c >= r);
                 okm |= ok ? (1u << (4 * i + jj)) : 0u;
-                a[i][jj] = ok ? __ldcg(pt + (size_t)i * n + 16 * jj) : 0.0;
+                a[i][jj] = ok ? sv_ld(pt + (size_t)i * n + 16 * jj, hint, pol) : 0.0;
             }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");      // everything below reads what the column kernel wrote
@@ -339,7 +363,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-                if (INTERIOR || (okm & (1u << (4 * i + jj)))) pt[(size_t)i * n + 16 * jj] = a[i][jj];
+                if (INTERIOR || (okm & (1u << (4 * i + jj)))) sv_st(pt + (size_t)i * n + 16 * jj, a[i][jj], hint, pol);
     }
 #ifdef TR_TIMING
     if (a[0][0] == 1.2345e300) return;       // (forces the tile loads to have landed before the stamp)
@@ -392,7 +416,8 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
 // stream but produced non-finite eigenvalues for single matrices when five host threads drove five solves
 // concurrently (bisected on the B200); not understood, so not used.
 __global__ void __launch_bounds__(256, 3)
-tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt)
+tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt,
+               int r_pin)
 {
     __shared__ SvSmem sm;
     // Boustrophedon sweep: consecutive launches walk the (matrix, tile) space in opposite directions, so a launch
@@ -409,8 +434,8 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
     TR_STAMP(1, 0);
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
-    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm);
-    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm);
+    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin);
+    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin);
 }
 
 // Tail of the tridiagonalisation: once the trailing block has at most TR_TAIL rows it fits in shared memory, and
@@ -1627,18 +1652,52 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         cfg.numAttrs = no_pdl ? 0 : 1;
         static int tr_old = -1;
         if (tr_old < 0) { const char* ev = getenv("GG_TR_OLD"); tr_old = ev ? atoi(ev) : 0; }
-        // blocked path (cluster panel kernel + DMMA rank-2k update) for TR_TAIL < n <= PB_NMAX; the per-column
-        // BLAS-2 chain below remains for larger matrices and as a cross-check (GG_TR_OLD=1)
-        const bool use_blocked = !tr_old && n > TR_TAIL && n <= PB_NMAX;
-        const int js = use_blocked ? n - TR_TAIL
-                                   : ((which == 1 || which == 2) ? n : (n > TR_TAIL ? n - TR_TAIL : 0));   // tail takes over at column js
+        // Stage 1 runs in up to three parts:
+        //   columns [0, jb)   blocked path (cluster panel kernel + DMMA rank-2k update, gg_sytrd_blocked.cuh);
+        //   columns [jb, js)  per-column chain (tr_col_kernel + tr_symv_kernel);
+        //   columns [js, n)   shared-memory tail.
+        // Measured on B200 (profiles/r02_sytrd_paths.json): at every batch shape tried the chain is as fast as or
+        // faster than the blocked path (K=20, p=1000: 11.6 vs 11.9 ms; K=2, p=1000: 5.4 vs 7.2 ms), so jb = 0 by
+        // default.  GG_TR_BLOCKED=1 uses the blocked path for every column below the tail, GG_TR_SWITCH_MB=x while
+        // the batch's upper triangles (4 M t^2 bytes) exceed x MB; GG_TR_OLD=1 disables it.
+        const int js_full = n > TR_TAIL ? n - TR_TAIL : 0;
+        const bool prof12 = (which == 1 || which == 2);
+        int jb = 0;
+        if (!tr_old && n > TR_TAIL && n <= PB_NMAX) {
+            const int nbp = sytrd_blocked_env("GG_TR_NB", 16) == 32 ? 32 : 16;
+            const double sw = (double)sytrd_blocked_env("GG_TR_SWITCH_MB", 1 << 20) * 1048576.0;
+            const bool all = sytrd_blocked_env("GG_TR_BLOCKED", 0) != 0;
+            while (jb < js_full && (all || 4.0 * M * (double)(n - jb - 1) * (n - jb - 1) > sw)) jb += nbp;
+            if (jb > js_full) jb = js_full;
+        }
+        const bool use_blocked = jb > 0;
+        // profiling variants: with a blocked part, which = 1 / 2 time its panel kernels / rank-2k updates alone;
+        // without one they time the column kernels / trailing-matrix passes of the chain over all columns (as before)
+        const int js = (prof12 && !use_blocked) ? n : js_full;       // the tail takes over at column js
         if (use_blocked) {
-            const int rc = sytrd_blocked_run(A, n, M, js, tw, Wpanel, skip, s, (which == 1 || which == 2) ? which : 0);
+            const int rc = sytrd_blocked_run(A, n, M, jb, tw, Wpanel, skip, s, prof12 ? which : 0);
             if (rc != 0) return rc;
+            if (jb < js && !prof12) {
+                // hand-over to the chain: nothing is pending, so the column kernel must find y = 0 (it then forms
+                // w_{jb-1} = 0) and a finite previous vector
+                tr_zero_kernel<<<dim3(1, M), 256, 0, s>>>(tw.y, (size_t)n, skip);
+                tr_zero_kernel<<<dim3(2, M), 256, 0, s>>>(tw.vbuf, (size_t)2 * n, skip);
+                gg_count_launch(2);
+            }
+        }
+        const bool chain = !(use_blocked && prof12) && jb < js;
+        // rows >= r_pin of every matrix are kept in L2 (evict_last) by the chain's trailing-matrix passes: the largest
+        // bottom-right triangle with 4 M (n - r_pin)^2 <= GG_TR_CHAIN_L2MB megabytes; -1: no hints
+        int r_pin = -1;
+        {
+            // (no measurable effect on the chain at K=20, p=1000 -- 12.05 vs 11.97 ms -- so it is off unless asked for;
+            //  the blocked path's streamed strips gain 3.5 ms from the same hints and use them by default)
+            const double l2b = (double)sytrd_blocked_env("GG_TR_CHAIN_L2MB", 0) * 1048576.0;
+            if (l2b > 0.0 && 4.0 * M * (double)n * n > l2b) r_pin = n - (int)floor(sqrt(l2b / (4.0 * M)));
         }
         const int lazy_q = gg_tr_lazy_depth();
-        int kb = 0;                                   // pairs kb..j-1 are pending at step j
-        for (int j = 0; j < js && !use_blocked; ++j) {
+        int kb = jb;                                  // pairs kb..j-1 are pending at step j
+        for (int j = jb; j < js && chain; ++j) {
             if (which != 2) {
                 const int len = n - j;
                 const int thr = len <= 2048 ? 256 : 512;
@@ -1659,12 +1718,12 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 const int nt = (t + SV_T - 1) / SV_T;
                 cfg.gridDim = dim3(nt * (nt + 1) / 2, M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
                 gg_count_launch(1);
-                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, kb, write, tw, (const int*)skip, nt);
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, kb, write, tw, (const int*)skip, nt, r_pin);
                 if (e != cudaSuccess) return (int)e;
             }
             if (write) kb = j;
         }
-        if (js < n && !(use_blocked && (which == 1 || which == 2))) {
+        if (js < n && !(use_blocked && prof12)) {
             const int ts = n - js;
             const size_t tsm = sizeof(double) * ((size_t)ts * (ts | 1) + 3 * ts + 64 + 4);
             static bool tattr = false;
@@ -1675,7 +1734,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
             }
             cfg.gridDim = dim3(M); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = tsm;
             gg_count_launch(1);
-            cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip, use_blocked ? 0 : 1);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip, chain ? 1 : 0);
             if (e != cudaSuccess) return (int)e;
         }
     }

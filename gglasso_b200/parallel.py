@@ -109,12 +109,12 @@ def ADMM_MGL_dist(S_local, lambda1, lambda2, reg, Omega_0_local, **kw):
     latent, mu1_local, group, check_every.
     Returns (sol_local, info); info = {'status', 'iterations', 'residual'} identical on every rank.
     """
-    from ._engine import to_host
+    from ._engine import to_host_many
     st, info = run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, **kw)
     latent = kw.get("latent", False)
     Omega = st.final_omega([info["iterations"]])
-    sol = {"Omega": to_host(Omega), "Theta": to_host(st.Theta), "X": to_host(st.X),
-           "L": to_host(st.L) if latent else np.zeros_like(S_local)}
+    outs = to_host_many([Omega, st.Theta, st.X] + ([st.L] if latent else []))
+    sol = {"Omega": outs[0], "Theta": outs[1], "X": outs[2], "L": outs[3] if latent else np.zeros_like(S_local)}
     return sol, info
 
 

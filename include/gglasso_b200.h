@@ -69,6 +69,9 @@ int gg_sytrd_profile(double* A, double* D, int M, int p, void* ws, size_t ws_byt
  * updates are pending (every q-th pass moves 16 B per element, the others 8 B).  Needed to state the algorithmic
  * bytes of a launch; 1 <= q <= 4 (environment GG_TR_LAZY, default 3). */
 int gg_sytrd_write_depth(void);
+/* diagnostics (GG_TR_TIMING=1): nanoseconds per phase of the blocked tridiagonalisation's panel kernel, summed by one
+ * CTA since the last call (16 counters, see gg_sytrd_blocked.cuh); reads and clears. */
+int gg_sytrd_phase_clock(unsigned long long* out16);
 
 /* Out = V diag(f(D)) V^T with V^T = Vt from gg_eigh (FP64 tensor cores, exactly symmetric result).
  * mode 0: f = phi+(d, beta) = (sqrt(d^2+4 beta)+d)/2   src/gglasso/solver/ggl_helper.py:272-303

@@ -72,16 +72,45 @@ if __name__ == "__main__":
     sizes = [(2, 145), (3, 200), (2, 333), (20, 500), (5, 777), (20, 1000), (1, 1289), (2, 2047)]
     if not old:
         for M, p in sizes:
-            check(M, p, {})
-        check(3, 400, {"GG_TR_NB": 32})
-        check(3, 400, {"GG_TR_CS": 4})
-        check(3, 400, {"GG_TR_CS": 8, "GG_TR_NB": 32})
-        check(2, 1000, {"GG_TR_CS": 16})
-        check(20, 1000, {"GG_TR_NB": 32})
+            check(M, p, {"GG_TR_BLOCKED": 1})                    # every column below the tail on the blocked path
+        check(20, 1000, {})                                       # default: per-column chain with L2 hints + tail
+        check(40, 1000, {})
+        check(3, 2500, {})
+        check(20, 1000, {"GG_TR_SWITCH_MB": 24})                  # blocked part + chain + tail
+        check(3, 400, {"GG_TR_NB": 32, "GG_TR_BLOCKED": 1})
+        check(3, 400, {"GG_TR_CS": 4, "GG_TR_BLOCKED": 1})
+        check(3, 400, {"GG_TR_CS": 8, "GG_TR_NB": 32, "GG_TR_SWITCH_MB": 1})
+        check(2, 1000, {"GG_TR_CS": 16, "GG_TR_SWITCH_MB": 4})
+        check(20, 1000, {"GG_TR_NB": 32, "GG_TR_SWITCH_MB": 30})
     else:
         check(20, 1000, {})
     for M, p, env in ([(20, 1000, {}), (10, 500, {}), (3, 1000, {}), (2, 1000, {}), (1, 1289, {})] if old else
-                      [(20, 1000, {}), (20, 1000, {"GG_TR_NB": 32}), (20, 1000, {"GG_TR_CS": 4}), (10, 500, {}),
-                       (10, 500, {"GG_TR_NB": 32}), (3, 1000, {}), (2, 1000, {}), (5, 1000, {}), (1, 1289, {}), (40, 1000, {})]):
+                      [(20, 1000, {}), (20, 1000, {"GG_TR_L2MB": 0}), (20, 1000, {"GG_TR_L2MB": 32}), (20, 1000, {"GG_TR_L2MB": 48}),
+                       (20, 1000, {"GG_TR_L2MB": 80}), (20, 1000, {"GG_TR_L2MB": 96}), (20, 1000, {"GG_TR_SWITCH_MB": 48}),
+                       (20, 1000, {"GG_TR_BLOCKED": 1}), (10, 500, {}), (3, 1000, {}),
+                       (40, 1000, {}), (40, 1000, {"GG_TR_L2MB": 0}), (40, 1000, {"GG_TR_L2MB": 96}),
+                       (10, 1000, {}), (10, 1000, {"GG_TR_L2MB": 0}), (5, 2000, {}), (5, 2000, {"GG_TR_L2MB": 0}), (1, 5000, {})]):
         timeit(M, p, env)
+    if not old:
+        names = ["X3", "householder+g", "strip product", "X1", "correction", "X2", "w+next row", "prologue", "epilogue"]
+        out["phases"] = []
+        for M, p, env in [(20, 1000, {"GG_TR_BLOCKED": 1})]:
+            os.environ["GG_TR_TIMING"] = "1"
+            for k, v in env.items():
+                os.environ[k] = str(v)
+            A = to_dev(sym(np.random.default_rng(1), M, p), dev)
+            e = Eigh(M, p, dev)
+            buf = (ctypes.c_ulonglong * 16)()
+            for rep in range(2):
+                W = A.clone()
+                torch.cuda.synchronize()
+                lib.gg_sytrd_phase_clock(buf)
+                lib.gg_sytrd_profile(_p(W), _p(e.D), M, p, _p(e.ws), e.ws_bytes, 0, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+            lib.gg_sytrd_phase_clock(buf)
+            rec = {"M": M, "p": p, "env": env, "ms": {nm: buf[i] / 1e6 for i, nm in enumerate(names)}}
+            print(rec, flush=True)
+            out["phases"].append(rec)
+            for k in list(env) + ["GG_TR_TIMING"]:
+                os.environ.pop(k, None)
     json.dump(out, open(path, "w"), indent=1)
