@@ -272,16 +272,23 @@ def main():
 
     # ---------------- end to end through the public API (host buffers), `steps` iterations -------------------------
     def public_call(max_iter, tol):
-        with contextlib.redirect_stdout(io.StringIO()):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
             if world == 1:
-                return ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=tol, rtol=tol,
-                                max_iter=max_iter)
-            sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K, tol=tol, rtol=tol,
-                                      max_iter=max_iter, check_every=10 ** 9 if tol == 0.0 else 1)
-            return sol, info
+                sol, info = ADMM_MGL(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, tol=tol, rtol=tol,
+                                     max_iter=max_iter)
+            else:
+                sol, info = ADMM_MGL_dist(S, cfg["lambda1"], cfg["lambda2"], cfg["reg"], Om0, K_total=K, tol=tol,
+                                          rtol=tol, max_iter=max_iter, check_every=10 ** 9 if tol == 0.0 else 1)
+        if "iterations" not in info:                   # the reference-signature call reports them in its printed line
+            words = buf.getvalue().split("ADMM terminated after ")[-1].split()
+            info = dict(info, iterations=int(words[0]) if words and words[0].isdigit() else None)
+        return sol, info
 
     dt = None
-    for rep in range(2):          # first call = warm-up (lazy kernel module loading, allocator); second is reported
+    sol = None
+    for rep in range(3):          # two warm-up calls (lazy module loading; the results live in page-locked memory from
+        del sol                   # torch's caching host allocator, which is filled by the first calls); third reported
         barrier()
         t0 = time.perf_counter()
         sol, info = public_call(steps, 0.0)
@@ -292,6 +299,7 @@ def main():
     d2h = 3 * S_full.nbytes / steps                                     # Omega, Theta, X of all ranks
 
     # ---------------- time to tolerance through the public API + parity against the reference fixture --------------
+    del sol
     barrier()
     t0 = time.perf_counter()
     sol, info = public_call(1000, 1e-7)

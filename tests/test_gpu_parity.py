@@ -593,8 +593,6 @@ def test_grid_search_device_resident_matches_host_driver():
     assert _rel(best_s["Theta"], best_d["Theta"]) < PER_ITER_TOL
 
 
-@pytest.mark.skipif(os.environ.get("GG_STRESS_TESTS", "0") != "1",
-                    reason="opt-in (GG_STRESS_TESTS=1): a failure here would poison the CUDA context for later tests")
 def test_grid_many_concurrent_columns_large_p():
     """eight columns on eight host threads / CUDA streams at a size that takes the full large-p eigensolver path
     (p >= 256: lazy-write sytrd with programmatic dependent launch, D&C, blocked back-transformation): the score
