@@ -468,8 +468,19 @@ def kernel_roofline(st, ms_per_step):
         if write:
             kb, n_write = j, n_write + 1
     achieved = total_bytes / (times[2] * 1e-3) / 1e9            # GB/s over all symv launches of one eigh
+    # DRAM traffic per launch from the committed ncu --set full capture (one read/read/write cycle at t = 640), scaled
+    # to the average launch by the ratio traffic / algorithmic bytes of the captured launches
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))["tr_symv_kernel"]
+        ratio = ((2 * tr["read_pass_dram_bytes"] + tr["write_pass_dram_bytes"]) /
+                 (2 * tr["algorithmic_read_pass_bytes"] + tr["algorithmic_write_pass_bytes"]))
+        traffic = ratio * total_bytes / n_launch
+        traffic_src = f"{ratio:.3f} x algorithmic, " + tr["source"]
+    except Exception:
+        pass
     return {"bound": "hbm", "kernel": "tr_symv_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-            "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "launches_per_step": n_launch, "write_depth": q, "write_passes": n_write,
             "avg_ms_per_launch": times[2] / n_launch,
             "algorithmic_bytes_per_launch_avg": total_bytes / n_launch,

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CTRL_STRIDE, HIST_STRIDE, NPART, C_DONE, C_ITER, C_RHO
+from ._lib import CTRL_STRIDE, HIST_STRIDE, NPART, C_DONE, C_ITER, C_RHO, C_STATUS, C_LAM1, C_LAM2
 
 
 # largest K of the fused tile-pair MGL prox (K x 272 doubles of shared memory per CTA <= 200 KB)
@@ -272,6 +272,31 @@ class AdmmState:
             self.pdim = to_dev((pv ** 2 + pv) / 2.0, dev)
         self.stream = torch.cuda.current_stream().cuda_stream
 
+    def reset(self, Omega_0, Theta_0=None, X_0=None, rho=1.0, lambdas=None):
+        """re-arm the state for another solve of the same shape on the same buffers (lambda grids): captured CUDA
+        graphs of the iteration stay valid.  ``lambdas`` = (lambda1, lambda2) go into the control block."""
+        if self.Omega is not self._bufA:
+            self.Omega, self.Omega_new = self._bufA, self._bufB
+        self.nswap = 0
+        self.Omega.copy_(Omega_0 if isinstance(Omega_0, torch.Tensor) else to_dev(Omega_0, self.dev))
+        if Theta_0 is None:
+            self.Theta.copy_(self.Omega)
+        else:
+            self.Theta.copy_(Theta_0 if isinstance(Theta_0, torch.Tensor) else to_dev(Theta_0, self.dev))
+        if X_0 is None:
+            self.X.zero_()
+        else:
+            self.X.copy_(X_0 if isinstance(X_0, torch.Tensor) else to_dev(X_0, self.dev))
+        if self.L is not None:
+            self.L.zero_()
+        ctrl = np.zeros((self.nprob, CTRL_STRIDE))
+        ctrl[:, C_RHO] = rho
+        ctrl[:, 1] = 1.0
+        if lambdas is not None:
+            ctrl[:, C_LAM1], ctrl[:, C_LAM2] = lambdas
+        self.ctrl.copy_(torch.from_numpy(ctrl), non_blocking=False)
+        self.hist.zero_()
+
     # -- one Omega step: W build, eigh, phi+ reconstruction into Omega_new -----------------
     def omega_step(self):
         lib, st = self.lib, self.stream
@@ -381,17 +406,33 @@ class AdmmState:
 def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None, lam_mat=None, rho=1.0,
              max_iter=1000, tol=1e-7, rtol=1e-4, stopping_criterion="boyd", update_rho=True, verbose=False,
              measure=False, latent=False, mu=None, nk=None, header=None, check_every=None, trace=None,
-             check_symmetric=False, pvec=None, Mblk=None, print_rho=False):
+             check_symmetric=False, pvec=None, Mblk=None, print_rho=False, state=None, graph=None):
     """Run the device ADMM loop.  ``kind``: 'mgl' (one problem of K matrices) or 'sgl' (M problems).
 
+    ``state``: an AdmmState of the same shapes from an earlier call (lambda grids): its buffers, workspace and captured
+    iteration graphs are reused.  ``graph``: run the iterations as replays of two captured CUDA graphs (one per
+    Omega ping-pong direction).  Off by default (GG_GRAPH=1 turns it on for p <= GG_GRAPH_MAX_P): measured on B200 the
+    loop is bound by the GPU-side latency of the eigensolver's dependent launches, not by the host -- cfg1 23.0 ms
+    eager vs 29.7 ms with capture + instantiation, cfg4 grid 2.65 s vs 2.60 s (profiles/r02_small_configs.json).
     Returns (state, info) where info carries iteration counts, status and histories (numpy).
     """
     S3 = S if S.ndim == 3 else S[None]       # numpy arrays or device tensors
     M, p, _ = S3.shape
     mpp = M if kind == "mgl" else 1
-    st = AdmmState(S3, Omega_0.reshape(S3.shape), None if Theta_0 is None else Theta_0.reshape(S3.shape),
-                   None if X_0 is None else X_0.reshape(S3.shape), mpp, rho, max_iter, latent, nk=nk, mu=mu,
-                   lam_mat=lam_mat, pvec=pvec)
+    if state is not None:
+        st = state
+        assert st.M == M and st.p == p and st.mpp == mpp and st.latent == latent and st.hist_cap >= max_iter
+        st.reset(Omega_0.reshape(S3.shape), None if Theta_0 is None else Theta_0.reshape(S3.shape),
+                 None if X_0 is None else X_0.reshape(S3.shape), rho,
+                 lambdas=(lambda1, lambda2) if kind == "mgl" else None)
+        st.stream = torch.cuda.current_stream().cuda_stream
+    else:
+        st = AdmmState(S3, Omega_0.reshape(S3.shape), None if Theta_0 is None else Theta_0.reshape(S3.shape),
+                       None if X_0 is None else X_0.reshape(S3.shape), mpp, rho, max_iter, latent, nk=nk, mu=mu,
+                       lam_mat=lam_mat, pvec=pvec)
+        if kind == "mgl":                        # lambdas live in the control block (see GG_C_LAM1)
+            st.ctrl[:, C_LAM1] = lambda1
+            st.ctrl[:, C_LAM2] = lambda2
     lib, stream = st.lib, st.stream
     nprob = st.nprob
     regi = {"GGL": 0, "FGL": 1}.get(reg, -1)
@@ -399,25 +440,40 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
         for A in (st.S, st.Omega, st.Theta, st.X):
             assert st.asym_max(A) <= 1e-5, "input X is not symmetric"
 
+    # MGL prox: the row-segment kernel (streams at the rate of the elementwise kernels) needs an exactly symmetric X --
+    # true for the default X_0 = 0 and for any X returned by a previous solve; an X_0 that is only symmetric up to
+    # rounding takes the tile-pair kernel, which mirrors the upper triangle exactly as the reference's prox_p does
+    prox_rows = False
     if kind == "mgl":
         nt = lib.gg_mgl_ntile(p)
         nparts_fused = nt * nt
+        if _env_int("GG_PROX_ROWS", 1) != 0 and M <= K_TILE_MAX:
+            prox_rows = (X_0 is None) or st.asym_max(st.X) == 0.0
+            if prox_rows:
+                nparts_fused = lib.gg_prox_mgl_rows_nparts(p)
     else:
         nparts_fused = lib.gg_sgl_nparts(p, M)
+    prox_mgl_fn = lib.gg_prox_mgl_rows if prox_rows else lib.gg_prox_mgl
     nparts_dual = lib.gg_sgl_nparts(p, M) * mpp
     # K beyond the shared-memory layout of the fused tile-pair prox (K x 272 doubles per CTA): the row-band prox of the
     # K-sharded path takes over on one device (pack -> band prox -> unpack fused with the dual update)
     big_K = kind == "mgl" and M > K_TILE_MAX
     nparts = nparts_dual if (latent or big_K) else nparts_fused
-    vband = tband = None
-    if big_K:
-        vband = torch.empty(M * p * p, dtype=torch.float64, device=st.dev)
-        tband = torch.zeros(M * p * p, dtype=torch.float64, device=st.dev)
-    partials = torch.zeros((nprob, max(nparts_fused, nparts_dual), NPART), dtype=torch.float64, device=st.dev)
-
-    blk_nrm = None
-    if Mblk is not None:
-        blk_nrm = torch.zeros((M, (p // Mblk) ** 2), dtype=torch.float64, device=st.dev)
+    if not hasattr(st, "_loopbuf"):          # loop buffers live with the state, so that captured graphs can be reused
+        vband = tband = blk_nrm = None
+        if big_K:
+            vband = torch.empty(M * p * p, dtype=torch.float64, device=st.dev)
+            tband = torch.zeros(M * p * p, dtype=torch.float64, device=st.dev)
+        nparts_cap = max(nparts_fused, nparts_dual, lib.gg_prox_mgl_rows_nparts(p) if kind == "mgl" else 0)
+        partials = torch.zeros((nprob, nparts_cap, NPART), dtype=torch.float64, device=st.dev)
+        if Mblk is not None:
+            blk_nrm = torch.zeros((M, (p // Mblk) ** 2), dtype=torch.float64, device=st.dev)
+        st._loopbuf = (vband, tband, partials, blk_nrm)
+        st._graphs = {}
+    vband, tband, partials, blk_nrm = st._loopbuf
+    if getattr(st, "_prox_rows_last", prox_rows) != prox_rows:
+        partials.zero_()                     # the two MGL prox kernels fill different subsets of the partial slots
+    st._prox_rows_last = prox_rows
     if check_every is None:
         check_every = 1 if (measure or verbose or p > 400) else 4
     runtime = np.zeros(max_iter)
@@ -437,7 +493,92 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             print("%4s\t%10s" % ("iter", "kkt residual"))
     printed = 0
 
-    for it in range(max_iter):
+    def iteration():
+        """one ADMM iteration enqueued on st.stream (the part of the loop below that has no host logic)"""
+        sm = st.stream
+        st.omega_step()
+        Cq = st.W if latent else None
+        if big_K:
+            _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), M, p, 1, _p(vband), sm),
+                       "gg_pack_bands")
+            _lib.check(lib.gg_prox_band(_p(vband), _p(tband), _p(st.ctrl), lambda1, lambda2, regi, M, p, p, 0, sm),
+                       "gg_prox_band")
+            _lib.check(lib.gg_unpack_dual(_p(tband), _p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta), _p(Cq),
+                                          _p(st.ctrl), M, p, 1, _p(partials), sm), "gg_unpack_dual")
+        elif kind == "mgl":
+            _lib.check(prox_mgl_fn(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(Cq),
+                                   _p(st.ctrl), lambda1, lambda2, regi, M, p, _p(partials), sm), "gg_prox_mgl")
+        elif Mblk is not None:
+            _lib.check(lib.gg_prox_fsgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(Cq),
+                                        _p(st.ctrl), float(lambda1), int(Mblk), M, p, _p(partials), _p(blk_nrm), sm),
+                       "gg_prox_fsgl")
+        else:
+            _lib.check(lib.gg_prox_sgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(Cq),
+                                       _p(st.ctrl), float(lambda1), _p(st.lam_mat), M, p, _p(partials), _p(st.pvec), sm),
+                       "gg_prox_sgl")
+        if latent:
+            st.l_step()
+            _lib.check(lib.gg_dual_update(_p(st.X), _p(st.Omega_new), _p(st.Omega), _p(st.Theta), _p(st.L),
+                                          _p(st.ctrl), M, p, mpp, 1 if kind == "sgl" else 0, _p(partials), sm),
+                       "gg_dual_update")
+        _lib.check(lib.gg_stop_update(_p(partials), nparts, _p(st.ctrl), _p(st.hist), st.hist_cap, _p(st.pdim),
+                                      tol, rtol, 1 if update_rho else 0, nprob, sm), "gg_stop_update")
+        st.swap()
+
+    if graph is None:
+        graph = p <= _env_int("GG_GRAPH_MAX_P", 640) and _env_int("GG_GRAPH", 0) != 0
+    use_graph = (graph and stopping_criterion == "boyd" and not measure and not verbose and trace is None
+                 and not _DEBUG_KEEP_INPUT and st.eig.nb2 == 0 and max_iter >= 4)
+    graph_done = False
+    first_eager = 0
+    if use_graph:
+        # lambdas are read from the control block by the MGL prox, so the key does not contain them for 'mgl'
+        key = (kind, regi, Mblk, latent, tol, rtol, update_rho, None if kind == "mgl" else float(lambda1), st.hist_cap,
+               prox_rows)
+        it = 0
+        graphs = st._graphs.get(key)
+        if graphs is None:
+            iteration()                          # first iteration eagerly: every kernel module is loaded before capture
+            it = 1
+            graphs = [None, None]
+            cap = torch.cuda.Stream(device=st.dev)
+            cap.wait_stream(torch.cuda.current_stream())
+            keep = (st.stream, st.nswap, st.Omega, st.Omega_new)
+            try:
+                with _H2D_LOCK:                  # one capture at a time (torch's capture bookkeeping is process wide)
+                    for _ in range(2):
+                        par = st.nswap % 2
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                            st.stream = torch.cuda.current_stream().cuda_stream
+                            iteration()
+                        graphs[par] = g
+            except Exception as ex:              # capture not possible here: run the loop eagerly, say so once
+                if not _STAGE.get("graph_warned"):
+                    _STAGE["graph_warned"] = True
+                    import warnings
+                    warnings.warn(f"gglasso_b200: CUDA graph capture of the ADMM iteration failed ({type(ex).__name__}: "
+                                  f"{str(ex)[:120]}); running eagerly")
+                graphs = False
+            # two captures = two pointer swaps: the pointers are back where they were, nothing has run
+            st.stream, st.nswap, st.Omega, st.Omega_new = keep
+            torch.cuda.current_stream().wait_stream(cap)
+            st._graphs[key] = graphs
+        if graphs is False:
+            use_graph = False
+            first_eager = it
+        while use_graph and it < max_iter:
+            graphs[st.nswap % 2].replay()
+            st.swap()
+            it += 1
+            if it % check_every == 0 or it == max_iter:
+                if np.all(st.read_ctrl()[:, C_DONE] != 0):
+                    break
+        if use_graph:
+            it_done = it
+            graph_done = True
+
+    for it in range(max_iter if graph_done else first_eager, max_iter):
         if measure:
             torch.cuda.synchronize()
             t0 = time.time()
@@ -459,8 +600,8 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             _lib.check(lib.gg_unpack_dual(_p(tband), _p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta), _p(C),
                                           _p(st.ctrl), M, p, 1, _p(partials), stream), "gg_unpack_dual")
         elif kind == "mgl":
-            _lib.check(lib.gg_prox_mgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
-                                       _p(st.ctrl), lambda1, lambda2, regi, M, p, _p(partials), stream),
+            _lib.check(prox_mgl_fn(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
+                                   _p(st.ctrl), lambda1, lambda2, regi, M, p, _p(partials), stream),
                        "gg_prox_mgl")
         elif Mblk is not None:
             _lib.check(lib.gg_prox_fsgl(_p(st.Omega_new), _p(st.Omega), _p(st.L), _p(st.X), _p(st.Theta), _p(C),
@@ -521,6 +662,11 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
 
     st.finish_x()
     ctrl = st.read_ctrl()
+    if stopping_criterion == "boyd" and np.any(ctrl[:, C_STATUS] < 0):
+        bad = np.flatnonzero(ctrl[:, C_STATUS] < 0).tolist()
+        raise _lib.GGLassoB200Error(f"non-finite residual in problem(s) {bad[:8]} after {int(ctrl[bad[0], C_ITER])} "
+                                    "iteration(s): the input is not finite or an eigendecomposition broke down "
+                                    "(numpy's eigh raises LinAlgError in the same situation)")
     info = {"ctrl": ctrl}
     if stopping_criterion == "boyd":
         iters = ctrl[:, C_ITER].astype(int)

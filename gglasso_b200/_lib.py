@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("GGLASSO_B200_LIB") or os.path.join(_HERE, "libgglasso
 CTRL_STRIDE = 16
 HIST_STRIDE = 5
 NPART = 5
-C_RHO, C_XSCALE, C_DONE, C_ITER, C_R, C_S, C_EPRI, C_EDUAL, C_STATUS = range(9)
+C_RHO, C_XSCALE, C_DONE, C_ITER, C_R, C_S, C_EPRI, C_EDUAL, C_STATUS, C_LAM1, C_LAM2 = range(11)
 
 _vp, _i, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
 
@@ -34,6 +34,8 @@ SIGNATURES = {
     "gg_prox_fsgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp, _vp]),
     "gg_mgl_ntile": (_i, [_i]),
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
+    "gg_prox_mgl_rows_nparts": (_i, [_i]),
+    "gg_prox_mgl_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "gg_pack_bands": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gg_unpack_dual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

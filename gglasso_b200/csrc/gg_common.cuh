@@ -18,6 +18,8 @@
 #define GG_C_EPRI     6
 #define GG_C_EDUAL    7
 #define GG_C_STATUS   8   // 1 = optimal (set together with DONE)
+#define GG_C_LAM1     9   // > 0: lambda1 of the MGL prox is taken from here instead of the kernel argument, so that a
+#define GG_C_LAM2     10  //      captured CUDA graph of the iteration can be replayed for another grid point
 
 #define GG_HIST_STRIDE 5  // r, s, e_pri, e_dual, rho (value used during the iteration)
 #define GG_NPART 5        // |Omega|^2, |Theta-L|^2, |X|^2, |Omega-Theta+L|^2, |Omega-Omega_prev|^2

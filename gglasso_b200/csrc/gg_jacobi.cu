@@ -432,14 +432,12 @@ static int launch_round(double* G, int M, int p, int nb, int round, double tol, 
     dim3 grid(nbe / 2, M);
     if ((p & 1) == 0) {
         auto k = bj_round_kernel<NB2, KC, true>;
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set on every call
         gg_count_launch(1);
         k<<<grid, 256, smem, s>>>(G, p, nb, round, tol, tol_in, inner_max, st);
     } else {
         auto k = bj_round_kernel<NB2, KC, false>;
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set on every call
         gg_count_launch(1);
         k<<<grid, 256, smem, s>>>(G, p, nb, round, tol, tol_in, inner_max, st);
     }
@@ -479,16 +477,14 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
     if (p <= small_max || (block_nb2 == 1 && p <= GG_SMALL_MAX)) {       // block_nb2 == 1 forces this path
         const int ld = p | 1;
         const size_t smem = sizeof(double) * (size_t)p * ld;
-        static bool attr = false;
         const int maxsm = (int)(sizeof(double) * GG_SMALL_MAX * (GG_SMALL_MAX | 1));
-        if (!attr) {
+        {   // the attribute is per device and cheap to set: no process-wide "done" flag
             cudaFuncSetAttribute(jacobi_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
             cudaFuncSetAttribute(jacobi_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
             cudaFuncSetAttribute(jacobi_small_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
             cudaFuncSetAttribute(jacobi_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
             cudaError_t e = cudaFuncSetAttribute(jacobi_small_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
             if (e != cudaSuccess) return (int)e;
-            attr = true;
         }
         // threads: 16 lanes per row pair; no more groups than pairs (rounded up to a warp multiple)
         int threads = ((p + 1) / 2) * JS_LP;

@@ -1726,12 +1726,8 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         if (js < n && !(use_blocked && prof12)) {
             const int ts = n - js;
             const size_t tsm = sizeof(double) * ((size_t)ts * (ts | 1) + 3 * ts + 64 + 4);
-            static bool tattr = false;
-            if (!tattr) {
-                cudaFuncSetAttribute(tr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(double) * ((size_t)TR_TAIL * (TR_TAIL | 1) + 3 * TR_TAIL + 68)));
-                tattr = true;
-            }
+            cudaFuncSetAttribute(tr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,       // (per device)
+                                 (int)(sizeof(double) * ((size_t)TR_TAIL * (TR_TAIL | 1) + 3 * TR_TAIL + 68)));
             cfg.gridDim = dim3(M); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = tsm;
             gg_count_launch(1);
             cudaError_t e = cudaLaunchKernelEx(&cfg, tr_tail_kernel, (const double*)A, n, js, tw, (const int*)skip, chain ? 1 : 0);
@@ -1755,10 +1751,10 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     static int bt_big = -1;
     if (bt_big < 0) {
         const char* ev = getenv("GG_BT_BIG");
-        cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
         bt_big = ev ? atoi(ev) : 1;
     }
+    cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                  // (per device)
+                         (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
     const bool use_big = npanels > 0 && which != 4 && bt_big && n >= BB_MIN;
     if (use_big) {
         const int nt64 = (n + BB_T - 1) / BB_T;
@@ -1788,12 +1784,8 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     GG_CHECK_LAUNCH();
     if (dbg_stage && dbg_nonfinite(dw.lam[L & 1], M, n, n, s)) return -14;
     {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(dc_secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr = true;
-        }
+        cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // (per device)
+        cudaFuncSetAttribute(dc_secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
     for (int l = L - 1; l >= 0; --l) {
         const int nodes = 1 << l;

@@ -124,7 +124,7 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
     """device loop of ADMM_MGL_dist; returns (AdmmState, info) without copying the solution to the host."""
     from . import _lib
     from ._engine import AdmmState, _p
-    from ._lib import C_DONE, C_ITER, NPART
+    from ._lib import C_DONE, C_ITER, C_STATUS, NPART
     assert reg in ['GGL', 'FGL'] and min(lambda1, lambda2) > 0 and rho > 0
     K_loc, p, _ = S_local.shape
     world = 1 if (group is False or not dist.is_initialized()) else dist.get_world_size(group)
@@ -192,6 +192,9 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
                 break
     st.finish_x()
     ctrl = st.read_ctrl()
+    if ctrl[0, C_STATUS] < 0:
+        raise _lib.GGLassoB200Error(f"non-finite residual after {int(ctrl[0, C_ITER])} iteration(s): the input is not "
+                                    "finite or an eigendecomposition broke down")
     n = int(ctrl[0, C_ITER])
     hist = st.hist[0, :n].cpu().numpy()
     r, s, e_pri, e_dual = hist[n - 1, :4]
@@ -318,11 +321,12 @@ def grid_search_device(S, N, reg, l1, l2, method="eBIC", gamma=0.1, tol=1e-7, rt
     def run_columns(cols, out):
         """one worker = one CUDA stream: its columns run back to back, warm starts stay on the device"""
         b, b_score, b_ix = None, np.inf, None
+        st = None                                 # one state per worker: buffers, workspace and iteration graphs are reused
         for g2 in cols:
             Omega_0 = eye
             for g1 in range(len(l2)):
                 st, res = run_admm("mgl", S_dev, Omega_0, None, None, lambda1=float(l1[g2]), lambda2=float(l2[g1]),
-                                   reg=reg, tol=tol, rtol=rtol, latent=latent, mu=mu)
+                                   reg=reg, tol=tol, rtol=rtol, latent=latent, mu=mu, state=st)
                 n = int(res["iters"][0])
                 Omega_0 = st.final_omega(res["iters"])
                 sc = _score_device(st, Omega_0, N, gamma, method)

@@ -31,6 +31,18 @@ def check_G(G, p):
     assert np.all(G[0, :, :] <= G[1, :, :]), "Only upper diagonal entries should be contained in G"
 
 
+def _assert_disjoint_groups(G):
+    """The group prox kernel handles all groups in parallel, which is the reference's sequential in-place loop
+    (ext_admm_solver.py:394-453) only if no entry (k, i, j) belongs to two groups -- what create_group_array /
+    construct_trivial_G produce.  Overlapping groups are rejected instead of being solved differently."""
+    Lg, K = G.shape[1], G.shape[2]
+    for k in range(K):
+        i, j = G[0, :, k], G[1, :, k]
+        m = i >= 0
+        key = i[m].astype(np.int64) * (int(G.max()) + 2) + j[m]
+        assert len(np.unique(key)) == len(key), f"instance {k}: an entry belongs to more than one group (unsupported)"
+
+
 def _pad(d, K, p, pm, fill_diag):
     out = np.zeros((K, pm, pm))
     for k in range(K):
@@ -77,6 +89,7 @@ def ext_ADMM_MGL(S: dict,
     assert min(lambda1.min(), lambda2) > 0
     assert reg in ['GGL']
     check_G(G, p)
+    _assert_disjoint_groups(G)
     assert rho > 0, "ADMM penalization parameter must be positive."
     assert stopping_criterion in ['boyd', 'kkt']
 

@@ -173,8 +173,12 @@ def _solve_components(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, allC, min
     small = [ci for ci in multi if len(allC[ci]) <= _BATCH_MAX] if batchable else []
     large = [ci for ci in multi if ci not in set(small)]
     for bucket in _size_buckets([len(allC[ci]) for ci in small]):
-        ids = [small[k] for k in bucket]
-        _solve_batch(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, [allC[ci] for ci in ids], ids, sol, lines, kw)
+        # a batch index travels in gridDim.y / .z (limit 65535) and every problem keeps a (max_iter, 5) residual
+        # history on the device: batches are cut so that both stay bounded
+        step = max(1, min(_BATCH_PROBLEMS_MAX, (256 << 20) // (40 * int(kw["max_iter"]))))
+        for lo in range(0, len(bucket), step):
+            ids = [small[k] for k in bucket[lo:lo + step]]
+            _solve_batch(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, [allC[ci] for ci in ids], ids, sol, lines, kw)
     for ci in large:
         C = allC[ci]
         ix = np.ix_(C, C)
@@ -196,6 +200,7 @@ def _solve_components(S, lambda1, lambda1_mask, Omega_0, Theta_0, X_0, allC, min
 
 
 _BATCH_MAX = 160          # GG_SMALL_MAX of the eigensolver
+_BATCH_PROBLEMS_MAX = 32768   # problems per ragged batch (grid dimension limit 65535)
 
 
 def _size_buckets(sizes):

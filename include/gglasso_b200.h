@@ -29,7 +29,9 @@ extern "C" {
 
 #define GG_CTRL_STRIDE 16 /* doubles per problem */
 /* ctrl[0]=rho  ctrl[1]=pending X scale  ctrl[2]=done  ctrl[3]=iterations done
- * ctrl[4..7]=r,s,eps_pri,eps_dual of the last iteration  ctrl[8]=1 if 'optimal' */
+ * ctrl[4..7]=r,s,eps_pri,eps_dual of the last iteration  ctrl[8]=1 if 'optimal'
+ * ctrl[9], ctrl[10]: if ctrl[9] > 0, lambda1 / lambda2 of gg_prox_mgl and gg_prox_band are read from here instead of
+ * the call arguments (lets a captured CUDA graph of one iteration serve every point of a lambda grid) */
 #define GG_HIST_STRIDE 5  /* per iteration: r, s, eps_pri, eps_dual, rho */
 #define GG_NPART 5        /* partial sums per CTA feeding gg_stop_update */
 
@@ -108,6 +110,15 @@ int gg_mgl_ntile(int p);
 int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
                 double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
                 double* partials, void* stream);
+
+/* Row-segment variant of gg_prox_mgl (same arguments and results): one CTA per (row, 256 columns) of the FULL matrix,
+ * every entry runs its own prox instead of mirroring the upper triangle.  Identical output -- exactly symmetric Theta --
+ * iff Omega (+L) and X are exactly symmetric, which the caller guarantees (Omega/L come from gg_recon; X stays
+ * symmetric when X_0 is); streams at the rate of the elementwise kernels.  partials: (gg_prox_mgl_rows_nparts(p), 5). */
+int gg_prox_mgl_rows_nparts(int p);
+int gg_prox_mgl_rows(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
+                     double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
+                     double* partials, void* stream);
 
 /* K-sharded MGL (one process per GPU): V = (Omega + L) + X on the local instances
  * (L may be NULL), and the cross-instance prox on a row band: V, Theta are (K, nb, p) slabs holding global rows

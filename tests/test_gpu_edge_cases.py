@@ -124,3 +124,19 @@ def test_nonconvergence_status_strings():
         assert info["status"] in ("max iterations reached", "primal optimal", "dual optimal", "optimal")
         assert f"after {rinfo['iterations']} iterations" in out
         assert _rel(sol["Theta"], ref["Theta"]) < TOL
+
+
+def test_non_finite_input_raises_instead_of_iterating():
+    """numpy's eigh raises LinAlgError on a non-finite matrix; here the device stopping test flags the non-finite
+    residual (status -1) and the host raises."""
+    from gglasso_b200 import ADMM_SGL, ADMM_MGL, GGLassoB200Error
+    rng = np.random.default_rng(0)
+    p = 20
+    S = np.cov(rng.standard_normal((p, 100)), bias=True)
+    S[3, 3] = np.nan
+    with pytest.raises(GGLassoB200Error, match="non-finite"):
+        _quiet(ADMM_SGL, S, 0.1, np.eye(p), max_iter=50)
+    S3 = np.stack([np.cov(rng.standard_normal((p, 100)), bias=True) for _ in range(2)])
+    S3[1, 0, 1] = S3[1, 1, 0] = np.inf
+    with pytest.raises((GGLassoB200Error, AssertionError)):
+        _quiet(ADMM_MGL, S3, 0.1, 0.1, "GGL", np.repeat(np.eye(p)[None], 2, 0), max_iter=50)

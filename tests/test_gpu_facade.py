@@ -131,3 +131,45 @@ def test_sgl_model_selection_takes_the_block_route():
     np.testing.assert_allclose(st_g["BIC"][0.1], st_c["BIC"][0.1], rtol=1e-6)
     assert st_c["BEST"] == st_g["BEST"]
     assert np.array_equal(Th_g != 0, Th_c != 0) and np.linalg.norm(Th_g - Th_c) <= 1e-6 * np.linalg.norm(Th_c)
+
+
+def test_device_scoring_matches_reference_helpers():
+    """gglasso_b200.scoring (eBIC / AIC incl. the lambda1_mask variant, robust_logdet's -inf rule, mean_sparsity,
+    matrix_rank, tune_threshold) against the reference's helpers (model_selection.py:697-894, utils.py:17-31)."""
+    ref.load()
+    from gglasso.helper import model_selection as ms
+    from gglasso.helper.utils import mean_sparsity
+    from gglasso_b200 import scoring
+    rng = np.random.default_rng(5)
+    K, pp, Ns = 3, 40, np.array([200, 300, 400])
+    A = rng.standard_normal((K, pp, 3 * pp))
+    S = A @ A.transpose(0, 2, 1) / (3 * pp)
+    Theta = np.linalg.inv(S + 0.5 * np.eye(pp))
+    Theta[np.abs(Theta) < 0.05] = 0.0
+    Theta = (Theta + Theta.transpose(0, 2, 1)) / 2
+    Sd, Td = torch.from_numpy(S).cuda(), torch.from_numpy(Theta).cuda()
+    for g in (0.0, 0.1, 0.7):
+        assert abs(scoring.ebic(Sd, Td, Ns, g) - ms.ebic(S, Theta, Ns, g)) <= 1e-9 * abs(ms.ebic(S, Theta, Ns, g))
+    assert abs(scoring.aic(Sd, Td, Ns) - ms.aic(S, Theta, Ns)) <= 1e-9 * abs(ms.aic(S, Theta, Ns))
+    mask = 0.5 + 0.5 * rng.random((pp, pp))
+    mask = (mask + mask.T) / 2
+    want = ms.ebic_single(S[0], Theta[0], 200, 0.3, lambda1_mask=mask)
+    assert abs(scoring.ebic(Sd[0], Td[0], 200, 0.3, lambda1_mask=mask) - want) <= 1e-9 * abs(want)
+    assert abs(scoring.mean_sparsity(Td) - mean_sparsity(Theta)) < 1e-15
+    # not positive definite -> -inf log det -> +inf score, as in robust_logdet
+    bad = Theta.copy()
+    bad[1] -= 10 * np.eye(pp)
+    assert scoring.ebic(Sd, torch.from_numpy(bad).cuda(), Ns, 0.1) == np.inf == ms.ebic(S, bad, Ns, 0.1)
+    # rank of low-rank PSD matrices
+    U = rng.standard_normal((K, pp, 4))
+    L = U @ U.transpose(0, 2, 1)
+    L[2] = 0.0
+    assert np.array_equal(scoring.matrix_rank(torch.from_numpy(L).cuda()), [np.linalg.matrix_rank(L[k]) for k in range(K)])
+    # threshold tuning
+    Tt, tau, sc = scoring.tune_threshold(Td[0], Sd[0], 200, method="eBIC", gamma=0.1)
+    Tr, taur, scr = ms.tune_threshold(Theta[0], S[0], 200, method="eBIC", gamma=0.1)
+    assert tau == taur and np.array_equal(Tt.cpu().numpy() != 0, Tr != 0)
+    np.testing.assert_allclose(sc, scr, rtol=1e-9)
+    Tm, taus, _ = scoring.tune_multiple_threshold(Td, Sd, Ns, None, method="AIC")
+    Tmr, tausr, _ = ms.tune_multiple_threshold(Theta, S, Ns, None, method="AIC")
+    assert np.array_equal(taus, tausr) and np.array_equal(Tm.cpu().numpy(), Tmr)
