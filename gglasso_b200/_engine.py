@@ -440,14 +440,16 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
         for A in (st.S, st.Omega, st.Theta, st.X):
             assert st.asym_max(A) <= 1e-5, "input X is not symmetric"
 
-    # MGL prox: the row-segment kernel (streams at the rate of the elementwise kernels) needs an exactly symmetric X --
-    # true for the default X_0 = 0 and for any X returned by a previous solve; an X_0 that is only symmetric up to
-    # rounding takes the tile-pair kernel, which mirrors the upper triangle exactly as the reference's prox_p does
+    # MGL prox: the row-segment kernel (GG_PROX_ROWS=1) needs an exactly symmetric X -- true for the default X_0 = 0 and
+    # for any X returned by a previous solve; an X_0 that is only symmetric up to rounding takes the tile-pair kernel,
+    # which mirrors the upper triangle exactly as the reference's prox_p does.  Off by default: measured on B200 it is
+    # slower (FGL 0.348 vs 0.296 ms, GGL 0.271 vs 0.253 ms at cfg3) -- it repeats the prox for the mirrored entries and
+    # its perfectly linear 2 KB runs do not buy the bandwidth back (profiles/r02_elementwise_bandwidth.json).
     prox_rows = False
     if kind == "mgl":
         nt = lib.gg_mgl_ntile(p)
         nparts_fused = nt * nt
-        if _env_int("GG_PROX_ROWS", 1) != 0 and M <= K_TILE_MAX:
+        if _env_int("GG_PROX_ROWS", 0) != 0 and M <= K_TILE_MAX:
             prox_rows = (X_0 is None) or st.asym_max(st.X) == 0.0
             if prox_rows:
                 nparts_fused = lib.gg_prox_mgl_rows_nparts(p)
