@@ -440,22 +440,12 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
         for A in (st.S, st.Omega, st.Theta, st.X):
             assert st.asym_max(A) <= 1e-5, "input X is not symmetric"
 
-    # MGL prox: the row-segment kernel (GG_PROX_ROWS=1) needs an exactly symmetric X -- true for the default X_0 = 0 and
-    # for any X returned by a previous solve; an X_0 that is only symmetric up to rounding takes the tile-pair kernel,
-    # which mirrors the upper triangle exactly as the reference's prox_p does.  Off by default: measured on B200 it is
-    # slower (FGL 0.348 vs 0.296 ms, GGL 0.271 vs 0.253 ms at cfg3) -- it repeats the prox for the mirrored entries and
-    # its perfectly linear 2 KB runs do not buy the bandwidth back (profiles/r02_elementwise_bandwidth.json).
-    prox_rows = False
     if kind == "mgl":
         nt = lib.gg_mgl_ntile(p)
         nparts_fused = nt * nt
-        if _env_int("GG_PROX_ROWS", 0) != 0 and M <= K_TILE_MAX:
-            prox_rows = (X_0 is None) or st.asym_max(st.X) == 0.0
-            if prox_rows:
-                nparts_fused = lib.gg_prox_mgl_rows_nparts(p)
     else:
         nparts_fused = lib.gg_sgl_nparts(p, M)
-    prox_mgl_fn = lib.gg_prox_mgl_rows if prox_rows else lib.gg_prox_mgl
+    prox_mgl_fn = lib.gg_prox_mgl
     nparts_dual = lib.gg_sgl_nparts(p, M) * mpp
     # K beyond the shared-memory layout of the fused tile-pair prox (K x 272 doubles per CTA): the row-band prox of the
     # K-sharded path takes over on one device (pack -> band prox -> unpack fused with the dual update)
@@ -466,16 +456,12 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
         if big_K:
             vband = torch.empty(M * p * p, dtype=torch.float64, device=st.dev)
             tband = torch.zeros(M * p * p, dtype=torch.float64, device=st.dev)
-        nparts_cap = max(nparts_fused, nparts_dual, lib.gg_prox_mgl_rows_nparts(p) if kind == "mgl" else 0)
-        partials = torch.zeros((nprob, nparts_cap, NPART), dtype=torch.float64, device=st.dev)
+        partials = torch.zeros((nprob, max(nparts_fused, nparts_dual), NPART), dtype=torch.float64, device=st.dev)
         if Mblk is not None:
             blk_nrm = torch.zeros((M, (p // Mblk) ** 2), dtype=torch.float64, device=st.dev)
         st._loopbuf = (vband, tband, partials, blk_nrm)
         st._graphs = {}
     vband, tband, partials, blk_nrm = st._loopbuf
-    if getattr(st, "_prox_rows_last", prox_rows) != prox_rows:
-        partials.zero_()                     # the two MGL prox kernels fill different subsets of the partial slots
-    st._prox_rows_last = prox_rows
     if check_every is None:
         check_every = 1 if (measure or verbose or p > 400) else 4
     runtime = np.zeros(max_iter)
@@ -535,8 +521,7 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     first_eager = 0
     if use_graph:
         # lambdas are read from the control block by the MGL prox, so the key does not contain them for 'mgl'
-        key = (kind, regi, Mblk, latent, tol, rtol, update_rho, None if kind == "mgl" else float(lambda1), st.hist_cap,
-               prox_rows)
+        key = (kind, regi, Mblk, latent, tol, rtol, update_rho, None if kind == "mgl" else float(lambda1), st.hist_cap)
         it = 0
         graphs = st._graphs.get(key)
         if graphs is None:

@@ -34,8 +34,6 @@ SIGNATURES = {
     "gg_prox_fsgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp, _vp]),
     "gg_mgl_ntile": (_i, [_i]),
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
-    "gg_prox_mgl_rows_nparts": (_i, [_i]),
-    "gg_prox_mgl_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "gg_pack_bands": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gg_unpack_dual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -11,8 +11,6 @@ int gg_launch_dual_update(double*, const double*, const double*, const double*, 
                           int, int, int, double*, cudaStream_t);
 int gg_launch_prox_mgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
                        double, int, int, int, double*, cudaStream_t);
-int gg_launch_prox_mgl_rows(const double*, const double*, const double*, double*, double*, double*, const double*, double,
-                            double, int, int, int, double*, cudaStream_t);
 int gg_launch_stop_update(const double*, int, double*, double*, int, const double*, double, double, int, int,
                           cudaStream_t);
 int gg_launch_scale_pending(double*, double*, int, int, int, cudaStream_t);
@@ -113,15 +111,6 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
     if (K <= 0 || p <= 0 || reg < 0 || reg > 1) return -1;
     return gg_launch_prox_mgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lambda1, lambda2, reg, K, p, partials,
                               (cudaStream_t)stream);
-}
-
-int gg_prox_mgl_rows(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
-                     double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
-                     double* partials, void* stream)
-{
-    if (K <= 0 || p <= 0 || reg < 0 || reg > 1) return -1;
-    return gg_launch_prox_mgl_rows(Omega, Omega_prev, L, X, Theta, C, ctrl, lambda1, lambda2, reg, K, p, partials,
-                                   (cudaStream_t)stream);
 }
 
 int gg_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta, const double* L,

@@ -344,86 +344,6 @@ prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
 }
 
 // ------------------------------------------------------------------------------------------
-// MGL prox, row-segment variant: one CTA per (row i, 256 consecutive columns); thread = entry (i, j) of the FULL
-// matrix, its K-vector in shared memory ([k][tid], conflict free).  Every global access of the CTA is a 2 KB
-// contiguous run of one plane, so the kernel streams like the elementwise kernels, where the tile-pair kernel above
-// reads K x 5 planes in 128-byte pieces (DRAM row misses: 0.41-0.48 of the copy bandwidth).  The price: the entry
-// (j, i) repeats the prox of (i, j) instead of mirroring it, which gives the identical, exactly symmetric Theta iff
-// the inputs Omega (+L) and X are exactly symmetric -- Omega and L always are (mirrored reconstruction), X is when
-// X_0 is (it stays so under X += Omega - Theta); the host checks X_0 and falls back to the tile-pair kernel otherwise.
-#define PR_T 256
-template <int REG, bool LATENT>
-__global__ void __launch_bounds__(PR_T)
-prox_mgl_rows_kernel(const double* __restrict__ Omega, const double* __restrict__ Omega_prev,
-                     const double* __restrict__ L, double* __restrict__ X, double* __restrict__ Theta,
-                     double* __restrict__ C, const double* __restrict__ ctrl, double lambda1, double lambda2,
-                     int K, int p, double* __restrict__ partials)
-{
-    extern __shared__ double ysm[];                 // K * PR_T
-    __shared__ double scratch[GG_NPART * 32];
-    if (ctrl[GG_C_DONE] != 0.0) return;
-    const double inv_rho = 1.0 / ctrl[GG_C_RHO];
-    if (ctrl[GG_C_LAM1] > 0.0) { lambda1 = ctrl[GG_C_LAM1]; lambda2 = ctrl[GG_C_LAM2]; }
-    const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
-    const int i = blockIdx.y, j = blockIdx.x * PR_T + threadIdx.x;
-    const bool valid = j < p;
-    const size_t pp = (size_t)p * p, e = (size_t)i * p + j;
-    double* y = ysm + threadIdx.x;
-    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (valid) {
-#pragma unroll 8
-        for (int k = 0; k < K; ++k) {
-            double v = Omega[k * pp + e];
-            if (LATENT) v = v + L[k * pp + e];
-            v = v + X[k * pp + e];
-            y[k * PR_T] = v;
-        }
-        if (i != j) {
-            if (REG == 0) {            // GGL: group soft threshold of the l1-soft-thresholded vector
-                double ss = 0.0;
-                for (int k = 0; k < K; ++k) {
-                    const double u = gg_soft(y[k * PR_T], l1);
-                    y[k * PR_T] = u;
-                    ss += u * u;
-                }
-                const double nrm = sqrt(ss);
-                const double a = nrm > l2 ? nrm : l2;
-                const double f = a - l2;
-                for (int k = 0; k < K; ++k) y[k * PR_T] = (y[k * PR_T] * f) / a;
-            } else {                   // FGL: TV prox across k, then l1 soft threshold
-                gg_tv1d_inplace(y, K, PR_T, l2);
-                for (int k = 0; k < K; ++k) y[k * PR_T] = gg_soft(y[k * PR_T], l1);
-            }
-        }
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * pp + e;
-            const double om = Omega[o], x = X[o];
-            const double th = y[k * PR_T];
-            Theta[o] = th;
-            if (LATENT) {
-                C[o] = (th - x) - om;
-            } else {
-                const double pr = Omega_prev[o];
-                const double d1 = om - th;
-                const double xn = x + d1;                  // X += Omega - Theta (+ L = 0)
-                X[o] = xn;
-                const double d2 = om - pr;
-                acc[0] += om * om; acc[1] += th * th; acc[2] += xn * xn; acc[3] += d1 * d1; acc[4] += d2 * d2;
-            }
-        }
-    }
-    if (!LATENT) {
-        gg_block_sum<GG_NPART>(acc, scratch);
-        if (threadIdx.x == 0) {
-            double* out = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * GG_NPART;
-#pragma unroll
-            for (int q = 0; q < GG_NPART; ++q) out[q] = acc[q];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // Stopping test + rho update, one CTA per problem; deterministic (fixed-order) reduction.
 __global__ void __launch_bounds__(256)
 stop_update_kernel(const double* __restrict__ partials, int nparts, double* __restrict__ ctrl,
@@ -872,40 +792,6 @@ int gg_launch_prox_mgl(const double* Omega, const double* Omega_prev, const doub
     }
     return latent ? launch_prox_mgl_t<1, true>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st)
                   : launch_prox_mgl_t<1, false>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st);
-}
-
-extern "C" int gg_prox_mgl_rows_nparts(int p) { return p * ((p + PR_T - 1) / PR_T); }
-
-template <int REG, bool LATENT>
-static int launch_prox_mgl_rows_t(const double* Omega, const double* Omega_prev, const double* L, double* X,
-                                  double* Theta, double* C, const double* ctrl, double l1, double l2, int K, int p,
-                                  double* partials, cudaStream_t st)
-{
-    const size_t smem = (size_t)K * PR_T * sizeof(double);
-    if (smem > 200 * 1024) return -2;   // K too large for the shared-memory layout
-    auto kern = prox_mgl_rows_kernel<REG, LATENT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    dim3 grid((p + PR_T - 1) / PR_T, p);
-    gg_count_launch(1);
-    kern<<<grid, PR_T, smem, st>>>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials);
-    GG_CHECK_LAUNCH();
-    return 0;
-}
-
-int gg_launch_prox_mgl_rows(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
-                            double* C, const double* ctrl, double l1, double l2, int reg, int K, int p,
-                            double* partials, cudaStream_t st)
-{
-    const bool latent = (C != nullptr);
-    if (reg == 0) {
-        return latent ? launch_prox_mgl_rows_t<0, true>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st)
-                      : launch_prox_mgl_rows_t<0, false>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st);
-    }
-    return latent ? launch_prox_mgl_rows_t<1, true>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st)
-                  : launch_prox_mgl_rows_t<1, false>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st);
 }
 
 int gg_launch_stop_update(const double* partials, int nparts, double* ctrl, double* hist, int hist_cap,

@@ -406,13 +406,18 @@ def block_SGL_dist(S, lambda1, Omega_0, Theta_0=None, X_0=None, rho=1., max_iter
     with contextlib.redirect_stdout(io.StringIO()):
         sol = _solve_components(S, lambda1, mask, Omega_0, Theta_0, X_0, allC, mine, kw, solver=solver)
     if world > 1:
-        use_cuda = dist.get_backend(group) == "nccl"
-        for k in ("Omega", "Theta", "X"):
-            t = torch.from_numpy(sol[k])
-            if use_cuda:
-                t = t.cuda()
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            sol[k] = t.cpu().numpy()
+        # only the solved blocks travel (a few tens of MB at cfg5), not three dense p x p arrays: every rank sends the
+        # diagonal blocks of its components and scatters what it receives; singletons were computed by their owners too
+        mine_blocks = {ci: tuple(np.ascontiguousarray(sol[k][np.ix_(allC[ci], allC[ci])]) for k in ("Omega", "Theta", "X"))
+                       for ci in mine}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine_blocks, group=group)
+        for r, blocks in enumerate(gathered):
+            if r == rank:
+                continue
+            for ci, (om, th, xx) in blocks.items():
+                ix = np.ix_(allC[ci], allC[ci])
+                sol["Omega"][ix], sol["Theta"][ix], sol["X"][ix] = om, th, xx
     return sol
 
 

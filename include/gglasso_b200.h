@@ -111,15 +111,6 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
                 double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
                 double* partials, void* stream);
 
-/* Row-segment variant of gg_prox_mgl (same arguments and results): one CTA per (row, 256 columns) of the FULL matrix,
- * every entry runs its own prox instead of mirroring the upper triangle.  Identical output -- exactly symmetric Theta --
- * iff Omega (+L) and X are exactly symmetric, which the caller guarantees (Omega/L come from gg_recon; X stays
- * symmetric when X_0 is); streams at the rate of the elementwise kernels.  partials: (gg_prox_mgl_rows_nparts(p), 5). */
-int gg_prox_mgl_rows_nparts(int p);
-int gg_prox_mgl_rows(const double* Omega, const double* Omega_prev, const double* L, double* X, double* Theta,
-                     double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
-                     double* partials, void* stream);
-
 /* K-sharded MGL (one process per GPU): V = (Omega + L) + X on the local instances
  * (L may be NULL), and the cross-instance prox on a row band: V, Theta are (K, nb, p) slabs holding global rows
  * row0..row0+nb-1 of all K instances (after the all-to-all re-tile).  Same prox as gg_prox_mgl. */

@@ -28,20 +28,13 @@ for reg in ("GGL", "FGL"):
         lib.gg_prox_mgl(_p(st.Omega_new), _p(st.Omega), None, _p(st.X), _p(st.Theta), None, _p(st.ctrl), 0.05, 0.01, regi,
                         K, p, _p(parts), stream)
 
-    partsr = torch.zeros((lib.gg_prox_mgl_rows_nparts(p), NPART), dtype=torch.float64, device="cuda")
-
-    def prox_rows():
-        lib.gg_prox_mgl_rows(_p(st.Omega_new), _p(st.Omega), None, _p(st.X), _p(st.Theta), None, _p(st.ctrl), 0.05, 0.01,
-                             regi, K, p, _p(partsr), stream)
-
     def buildw():
         lib.gg_build_w(_p(st.Theta), None, _p(st.X), _p(st.S), None, _p(st.ctrl), K, p, K, _p(st.W), stream)
 
     def recon():
         lib.gg_recon(_p(st.W), _p(st.eig.D), None, _p(st.ctrl), K, 0, K, p, _p(st.Omega_new), stream)
 
-    for name, fn, nbytes in (("prox_mgl_" + reg, prox, 5 * A), ("prox_mgl_rows_" + reg, prox_rows, 5 * A),
-                             ("build_w", buildw, 4 * A)):
+    for name, fn, nbytes in (("prox_mgl_" + reg, prox, 5 * A), ("build_w", buildw, 4 * A)):
         ts = []
         for r in range(12):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -179,37 +179,6 @@ def test_prox_mgl_fused_dual_and_norms(reg, K, p):
     np.testing.assert_allclose(sums, ref, rtol=1e-12)
 
 
-@pytest.mark.parametrize("reg,K,p,latent", [("GGL", 2, 16, False), ("FGL", 5, 33, False), ("FGL", 20, 300, False),
-                                            ("GGL", 20, 257, False), ("FGL", 7, 260, True), ("GGL", 3, 513, True)])
-def test_prox_mgl_rows_kernel_equals_tile_pair_kernel(reg, K, p, latent):
-    """the row-segment MGL prox (every entry runs its own prox) against the tile-pair kernel (upper triangle mirrored):
-    bit-identical Theta / X / C on exactly symmetric inputs, same residual sums."""
-    from gglasso_b200 import _lib
-    from gglasso_b200._engine import to_dev, _p
-    lib = _lib.load()
-    dev = torch.device("cuda")
-    rng = np.random.default_rng(K * 1000 + p)
-    Om, Omp, X, Lm = (np.stack([_sym(rng, p, 0.3) for _ in range(K)]) for _ in range(4))
-    rho, l1, l2 = 0.5, 0.21, 0.13
-    regi = 0 if reg == "GGL" else 1
-    outs = []
-    for fn, nparts in ((lib.gg_prox_mgl, lib.gg_mgl_ntile(p) ** 2), (lib.gg_prox_mgl_rows, lib.gg_prox_mgl_rows_nparts(p))):
-        parts = torch.zeros((nparts, 5), dtype=torch.float64, device=dev)
-        dX, Th = to_dev(X, dev), torch.zeros((K, p, p), dtype=torch.float64, device=dev)
-        Cd = torch.zeros_like(Th) if latent else None
-        rc = fn(_p(to_dev(Om, dev)), _p(to_dev(Omp, dev)), _p(to_dev(Lm, dev)) if latent else None, _p(dX), _p(Th), _p(Cd),
-                _p(_ctrl(dev, rho)), l1, l2, regi, K, p, _p(parts), 0)
-        assert rc == 0
-        outs.append((Th.cpu().numpy(), dX.cpu().numpy(), None if Cd is None else Cd.cpu().numpy(), parts.sum(0).cpu().numpy()))
-    (t0, x0, c0, s0), (t1, x1, c1, s1) = outs
-    assert np.array_equal(t0, t1) and np.array_equal(x0, x1)
-    assert np.array_equal(t1, t1.transpose(0, 2, 1))
-    if latent:
-        assert np.array_equal(c0, c1)
-    else:
-        np.testing.assert_allclose(s1, s0, rtol=1e-12)
-
-
 @pytest.mark.parametrize("p,masked", [(1, False), (7, False), (100, True), (257, False)])
 def test_prox_sgl_kernel(p, masked):
     from gglasso_b200 import _lib
