@@ -134,3 +134,80 @@ def tune_multiple_threshold(Theta, S, N, tau_range=None, method="eBIC", gamma=0.
     for k in range(K):
         out[k], tau[k], score[k] = tune_threshold(Theta[k], S[k], float(Nv[k]), tau_range, method, gamma)
     return out, tau, score
+
+
+DEFAULT_GAMMAS = [0.1, 0.3, 0.5, 0.7]      # model_selection.py:17
+
+
+def single_grid_search_device(S, lambda_range, N, method="eBIC", gamma=0.3, latent=False, mu_range=None,
+                              thresholding_=False, store_all=True, tol=1e-7, rtol=1e-7, lambda1_mask=None):
+    """Device-resident statement of the reference's ``single_grid_search(..., use_block=False)``
+    (src/gglasso/helper/model_selection.py:505-690): the lambda1 (x mu1) path of the single graphical lasso with S,
+    the warm starts and every scored Theta / L staying on the GPU; scores (eBIC for all default gammas, AIC), sparsity,
+    rank of L and the optional threshold tuning come from this module.  Same loop order, same start points
+    (Omega_0 <- previous Omega, X_0 = identity at every point), same return layout:
+    ``(best_sol, estimates, lowrank, stats)`` with numpy arrays.  (The block-wise route of the reference,
+    ``use_block=True``, stays on the host path: ``install()`` + the reference's own driver.)"""
+    from ._engine import run_admm, require_cuda, to_dev, to_host_many
+    dev = require_cuda()
+    S = np.asarray(S, dtype=np.float64)
+    p = S.shape[0]
+    if latent:
+        assert mu_range is not None
+        mu_range = np.asarray(mu_range, dtype=np.float64)
+    else:
+        mu_range = np.array([0])
+    lambda_range = np.asarray(lambda_range, dtype=np.float64)
+    _L, _M = len(lambda_range), len(mu_range)
+    gammas = sorted(set(DEFAULT_GAMMAS + [gamma]))
+    MU, LAMB = np.meshgrid(mu_range, lambda_range)
+    BIC = {g: np.nan * np.zeros((_L, _M)) for g in gammas}
+    AIC = np.nan * np.zeros((_L, _M))
+    SP = np.nan * np.zeros((_L, _M))
+    RANK = np.zeros((_L, _M))
+    TAU = np.zeros((_L, _M)) if thresholding_ else None
+    estimates = np.zeros((_L, _M, p, p)) if store_all else None
+    lowrank = np.zeros((_L, _M, p, p)) if store_all else None
+    S_dev = to_dev(S, dev)[None] if S.nbytes >= (8 << 20) else torch.from_numpy(S).to(dev)[None]
+    eye = torch.eye(p, dtype=torch.float64, device=dev)[None]
+    mask_dev = None if lambda1_mask is None else torch.as_tensor(np.asarray(lambda1_mask, dtype=np.float64), device=dev)
+    Omega_0 = eye
+    eig = Eigh(1, p, dev)
+    best, curr_min = None, np.inf
+    for j in range(_L):
+        lam_mat = None if mask_dev is None else (float(lambda_range[j]) * mask_dev)[None].contiguous()
+        for m in range(_M):
+            st, res = run_admm("sgl", S_dev, Omega_0, None, eye, lambda1=float(lambda_range[j]), lam_mat=lam_mat,
+                               tol=tol, rtol=rtol, latent=latent, mu=np.array([mu_range[m]]) if latent else None)
+            Omega_0 = st.final_omega(res["iters"])
+            Theta = st.Theta[0]
+            if latent:
+                RANK[j, m] = matrix_rank(st.L, eig)[0]
+                if store_all:
+                    lowrank[j, m] = st.L[0].cpu().numpy()
+            if thresholding_:
+                Theta, TAU[j, m], _ = tune_threshold(Theta, S_dev[0], N, None, method, gamma)
+            AIC[j, m] = aic(S_dev[0], Theta, N, eig=eig)
+            for g in gammas:
+                BIC[g][j, m] = ebic(S_dev[0], Theta, N, g, lambda1_mask=lambda1_mask, eig=eig)
+            SP[j, m] = mean_sparsity(Theta)
+            if store_all:
+                estimates[j, m] = Theta.cpu().numpy()
+            score = BIC[gamma][j, m] if method == "eBIC" else AIC[j, m]
+            if score < curr_min:
+                curr_min = score
+                best = {"Omega": Omega_0[0].clone(), "Theta": Theta.clone(), "X": st.X[0].clone(),
+                        "L": st.L[0].clone() if latent else None}
+    AIC[AIC == -np.inf] = np.nan
+    for g in gammas:
+        BIC[g][BIC[g] == -np.inf] = np.nan
+    table = AIC if method == "AIC" else BIC[gamma]
+    ix = np.unravel_index(np.nanargmin(table), table.shape)
+    stats = {"BIC": BIC, "AIC": AIC, "SP": SP, "RANK": RANK, "LAMBDA": LAMB, "MU": MU, "TAU": TAU,
+             "BEST": {"lambda1": LAMB[ix], "mu1": MU[ix]}, "GAMMA": gammas}
+    best_sol = {}
+    if best is not None:
+        keys = [k for k in ("Omega", "Theta", "X", "L") if best[k] is not None]
+        for k, a in zip(keys, to_host_many([best[k] for k in keys])):
+            best_sol[k] = a
+    return best_sol, estimates, lowrank, stats

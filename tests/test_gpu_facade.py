@@ -173,3 +173,32 @@ def test_device_scoring_matches_reference_helpers():
     Tm, taus, _ = scoring.tune_multiple_threshold(Td, Sd, Ns, None, method="AIC")
     Tmr, tausr, _ = ms.tune_multiple_threshold(Theta, S, Ns, None, method="AIC")
     assert np.array_equal(taus, tausr) and np.array_equal(Tm.cpu().numpy(), Tmr)
+
+
+@pytest.mark.parametrize("latent", [False, True])
+def test_single_grid_search_on_device_matches_reference_driver(latent):
+    """scoring.single_grid_search_device (S, warm starts, scoring on the GPU) against the reference's
+    single_grid_search(use_block=False) on its CPU solver (model_selection.py:505-690)."""
+    ref.load()
+    import gglasso_b200
+    gglasso_b200.uninstall()
+    from gglasso.helper import data_generation as dg
+    from gglasso.helper.model_selection import single_grid_search
+    from gglasso_b200.scoring import single_grid_search_device
+    Sigma, _ = dg.generate_precision_matrix(p=40, M=2, style="powerlaw", gamma=2.8, prob=0.1, seed=99)
+    S, _ = dg.sample_covariance_matrix(Sigma, 500, seed=99)
+    lam = np.logspace(-0.5, -2, 5)
+    mu = np.logspace(0, -1, 3) if latent else None
+    kw = dict(method="eBIC", gamma=0.3, latent=latent, mu_range=mu, store_all=True, tol=1e-8, rtol=1e-8)
+    bs_r, est_r, low_r, st_r = _quiet(single_grid_search, S, lam, 500, use_block=False, **kw)
+    bs_g, est_g, low_g, st_g = _quiet(single_grid_search_device, S, lam, 500, **kw)
+    assert st_r["BEST"] == st_g["BEST"]
+    for g in st_r["BIC"]:
+        np.testing.assert_allclose(st_g["BIC"][g], st_r["BIC"][g], rtol=1e-7)
+    np.testing.assert_allclose(st_g["AIC"], st_r["AIC"], rtol=1e-7)
+    assert np.array_equal(st_g["SP"], st_r["SP"]) and np.array_equal(st_g["RANK"], st_r["RANK"])
+    assert np.abs(est_g - est_r).max() < 1e-6 and np.array_equal(est_g != 0, est_r != 0)
+    if latent:
+        assert np.abs(low_g - low_r).max() < 1e-6
+    for k in bs_r:
+        assert np.abs(bs_g[k] - bs_r[k]).max() < 1e-6, k
