@@ -298,10 +298,14 @@ class AdmmState:
         self.hist.zero_()
 
     # -- one Omega step: W build, eigh, phi+ reconstruction into Omega_new -----------------
-    def omega_step(self):
+    def omega_step(self, upper=False):
         lib, st = self.lib, self.stream
-        _lib.check(lib.gg_build_w(_p(self.Theta), _p(self.L), _p(self.X), _p(self.S), _p(self.nk), _p(self.ctrl),
-                                  self.M, self.p, self.mpp, _p(self.W), st), "gg_build_w")
+        if upper:       # upper triangles only (see run_admm): the tridiagonal eigensolver reads nothing else of W
+            _lib.check(lib.gg_build_w_upper(_p(self.Theta), _p(self.X), _p(self.S), _p(self.nk), _p(self.ctrl),
+                                            self.M, self.p, _p(self.W), st), "gg_build_w_upper")
+        else:
+            _lib.check(lib.gg_build_w(_p(self.Theta), _p(self.L), _p(self.X), _p(self.S), _p(self.nk), _p(self.ctrl),
+                                      self.M, self.p, self.mpp, _p(self.W), st), "gg_build_w")
         self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st, warm=self.warm_w)
         self.eig.recon(self.W, self.Omega_new, 0, bnum=self.nk, ctrl=self.ctrl, mpp=self.mpp, stream=st)
 
@@ -310,6 +314,11 @@ class AdmmState:
         st = self.stream
         self.eig.eigh(self.W, ctrl=self.ctrl, mpp=self.mpp, stream=st, warm=self.warm_c)
         self.eig.recon(self.W, self.L, 1, bnum=self.mu, ctrl=self.ctrl, mpp=self.mpp, stream=st)
+
+    def mirror(self):
+        """fill the lower triangles of Theta and X from the upper ones (after iterations that ran on the upper
+        triangles only)"""
+        _lib.check(self.lib.gg_mirror_upper(_p(self.Theta), _p(self.X), self.M, self.p, self.stream), "gg_mirror_upper")
 
     def swap(self):
         self.Omega, self.Omega_new = self.Omega_new, self.Omega
@@ -450,13 +459,23 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     # K beyond the shared-memory layout of the fused tile-pair prox (K x 272 doubles per CTA): the row-band prox of the
     # K-sharded path takes over on one device (pack -> band prox -> unpack fused with the dual update)
     big_K = kind == "mgl" and M > K_TILE_MAX
+    # Non-latent MGL on the tridiagonal eigensolver path: the iterations keep only the UPPER triangles of Theta, X and W
+    # current (every consumer inside the loop reads nothing else; half the elementwise HBM traffic) and the lower
+    # triangles are filled once after the loop -- prox_p's mirroring (ggl_helper.py:198-205) done once.
+    upper = (kind == "mgl" and not latent and not big_K and stopping_criterion == "boyd" and not measure
+             and not _DEBUG_KEEP_INPUT and st.eig.nb2 == 0 and p > _env_int("GG_JACOBI_MAX", 48)
+             and _env_int("GG_UPPER", 1) != 0)
+    nparts_upper = lib.gg_mgl_upper_nparts(p) if kind == "mgl" else 0
+    if upper:
+        nparts_fused = nparts_upper
     nparts = nparts_dual if (latent or big_K) else nparts_fused
     if not hasattr(st, "_loopbuf"):          # loop buffers live with the state, so that captured graphs can be reused
         vband = tband = blk_nrm = None
         if big_K:
             vband = torch.empty(M * p * p, dtype=torch.float64, device=st.dev)
             tband = torch.zeros(M * p * p, dtype=torch.float64, device=st.dev)
-        partials = torch.zeros((nprob, max(nparts_fused, nparts_dual), NPART), dtype=torch.float64, device=st.dev)
+        partials = torch.zeros((nprob, max(nparts_fused, nparts_dual, nparts_upper), NPART), dtype=torch.float64,
+                               device=st.dev)
         if Mblk is not None:
             blk_nrm = torch.zeros((M, (p // Mblk) ** 2), dtype=torch.float64, device=st.dev)
         st._loopbuf = (vband, tband, partials, blk_nrm)
@@ -484,9 +503,12 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     def iteration():
         """one ADMM iteration enqueued on st.stream (the part of the loop below that has no host logic)"""
         sm = st.stream
-        st.omega_step()
+        st.omega_step(upper)
         Cq = st.W if latent else None
-        if big_K:
+        if upper:
+            _lib.check(lib.gg_prox_mgl_upper(_p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta), _p(st.ctrl),
+                                             lambda1, lambda2, regi, M, p, _p(partials), sm), "gg_prox_mgl_upper")
+        elif big_K:
             _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), M, p, 1, _p(vband), sm),
                        "gg_pack_bands")
             _lib.check(lib.gg_prox_band(_p(vband), _p(tband), _p(st.ctrl), lambda1, lambda2, regi, M, p, p, 0, sm),
@@ -569,7 +591,7 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
         if measure:
             torch.cuda.synchronize()
             t0 = time.time()
-        st.omega_step()
+        st.omega_step(upper)
         if _DEBUG_KEEP_INPUT:
             _debug_check(st, it, "after omega_step", D=st.eig.D, Vt=st.W, Omega_new=st.Omega_new)
         if measure and kind == "mgl":
@@ -579,7 +601,10 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
             Dw = st.eig.D
             logdet_dev = torch.log(0.5 * (torch.sqrt(Dw * Dw + 4 * beta[:, None]) + Dw)).sum()
         C = st.W if latent else None
-        if big_K:
+        if upper:
+            _lib.check(lib.gg_prox_mgl_upper(_p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta), _p(st.ctrl),
+                                             lambda1, lambda2, regi, M, p, _p(partials), stream), "gg_prox_mgl_upper")
+        elif big_K:
             _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), M, p, 1, _p(vband), stream),
                        "gg_pack_bands")
             _lib.check(lib.gg_prox_band(_p(vband), _p(tband), _p(st.ctrl), lambda1, lambda2, regi, M, p, p, 0, stream),
@@ -619,8 +644,12 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
                 if st.ctrl[0, C_DONE].item() != 0 and st.ctrl[0, C_ITER].item() != it + 1:
                     pass
                 elif callable(trace):
+                    if upper:
+                        st.mirror()
                     trace(st, it)
                 else:
+                    if upper:
+                        st.mirror()
                     trace.append(dict(Omega=st.Omega.cpu().numpy(), Theta=st.Theta.cpu().numpy(),
                                       L=None if st.L is None else st.L.cpu().numpy(), X=st.X.cpu().numpy()))
             if (it + 1) % check_every == 0 or it + 1 == max_iter:
@@ -648,6 +677,8 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
                 break
 
     st.finish_x()
+    if upper:
+        st.mirror()
     ctrl = st.read_ctrl()
     if stopping_criterion == "boyd" and np.any(ctrl[:, C_STATUS] < 0):
         bad = np.flatnonzero(ctrl[:, C_STATUS] < 0).tolist()

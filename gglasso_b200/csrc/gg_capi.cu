@@ -11,6 +11,11 @@ int gg_launch_dual_update(double*, const double*, const double*, const double*, 
                           int, int, int, double*, cudaStream_t);
 int gg_launch_prox_mgl(const double*, const double*, const double*, double*, double*, double*, const double*, double,
                        double, int, int, int, double*, cudaStream_t);
+int gg_launch_prox_mgl_upper(const double*, const double*, double*, double*, const double*, double, double, int, int,
+                             int, double*, cudaStream_t);
+int gg_launch_build_w_upper(const double*, double*, const double*, const double*, const double*, int, int, double*,
+                            cudaStream_t);
+int gg_launch_mirror_upper(double*, double*, int, int, cudaStream_t);
 int gg_launch_stop_update(const double*, int, double*, double*, int, const double*, double, double, int, int,
                           cudaStream_t);
 int gg_launch_scale_pending(double*, double*, int, int, int, cudaStream_t);
@@ -111,6 +116,27 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
     if (K <= 0 || p <= 0 || reg < 0 || reg > 1) return -1;
     return gg_launch_prox_mgl(Omega, Omega_prev, L, X, Theta, C, ctrl, lambda1, lambda2, reg, K, p, partials,
                               (cudaStream_t)stream);
+}
+
+int gg_prox_mgl_upper(const double* Omega, const double* Omega_prev, double* X, double* Theta, const double* ctrl,
+                      double lambda1, double lambda2, int reg, int K, int p, double* partials, void* stream)
+{
+    if (K <= 0 || p <= 0 || reg < 0 || reg > 1) return -1;
+    return gg_launch_prox_mgl_upper(Omega, Omega_prev, X, Theta, ctrl, lambda1, lambda2, reg, K, p, partials,
+                                    (cudaStream_t)stream);
+}
+
+int gg_build_w_upper(const double* Theta, double* X, const double* S, const double* nk, const double* ctrl, int K,
+                     int p, double* W, void* stream)
+{
+    if (K <= 0 || p <= 0) return -1;
+    return gg_launch_build_w_upper(Theta, X, S, nk, ctrl, K, p, W, (cudaStream_t)stream);
+}
+
+int gg_mirror_upper(double* A0, double* A1, int M, int p, void* stream)
+{
+    if (M <= 0 || p <= 0 || A0 == nullptr) return -1;
+    return gg_launch_mirror_upper(A0, A1, M, p, (cudaStream_t)stream);
 }
 
 int gg_dual_update(double* X, const double* Omega, const double* Omega_prev, const double* Theta, const double* L,

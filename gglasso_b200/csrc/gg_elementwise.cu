@@ -344,6 +344,154 @@ prox_mgl_kernel(const double* __restrict__ Omega, const double* __restrict__ Ome
 }
 
 // ------------------------------------------------------------------------------------------
+// W build on the upper triangle only (companion of prox_mgl_upper_kernel; non-latent MGL).  Rows i and p-1-i are
+// handled by the same CTA (p+1 entries together), columns start at the 256-byte boundary left of the diagonal.
+__global__ void __launch_bounds__(EW_THREADS)
+build_w_upper_kernel(const double* __restrict__ Theta, double* __restrict__ X, const double* __restrict__ S,
+                     const double* __restrict__ nk, const double* __restrict__ ctrl, int p, double* __restrict__ W)
+{
+    const int m = blockIdx.y;
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const double rho = ctrl[GG_C_RHO];
+    const double xs = ctrl[GG_C_XSCALE];
+    const double beta = (nk ? nk[m] : 1.0) / rho;
+    const bool rescale = (xs != 1.0);
+    const size_t base = (size_t)m * p * p;
+    const int half = (p + 1) / 2;
+    for (int r = blockIdx.x; r < half; r += gridDim.x) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int i = side ? p - 1 - r : r;
+            if (side && i == r) break;
+            const size_t row = base + (size_t)i * p;
+            for (int j = (i & ~31) + threadIdx.x; j < p; j += EW_THREADS) {
+                if (j < i) continue;
+                const double x = X[row + j];
+                const double xv = rescale ? xs * x : x;
+                double w = Theta[row + j];
+                w = w - xv;
+                w = w - beta * S[row + j];
+                W[row + j] = w;
+                if (rescale) X[row + j] = xv;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// MGL prox on the UPPER triangle only (non-latent loop).  Every array of the iteration is symmetric, and the kernels
+// that consume Theta and X inside the loop need their upper triangles only: build_w forms W entry by entry and the
+// tridiagonal eigensolver reads the upper triangle of W; the residual norms are sums in which an off-diagonal entry
+// counts twice.  So the loop keeps the upper triangles of Theta and X current (2.5 A bytes instead of 5 A) and
+// mirror_upper_kernel fills the lower ones once, after the last iteration -- the same mirroring prox_p does
+// (ggl_helper.py:190-207), done once instead of every iteration.
+// One CTA per tile of UT_R rows x UT_C columns: a warp reads 256 contiguous bytes per k-slice, a CTA row 256 B; CTAs
+// that are resident together continue the same rows.  Thread t owns one entry; its K-vector lives in shared memory at
+// [k][t] (distinct banks for any per-thread k, which the data-dependent TV scan needs).
+#define UT_R 8
+#define UT_C 32
+#define UT_THREADS (UT_R * UT_C)
+
+__host__ __device__ inline int ut_ntiles(int p)
+{
+    const int nr = (p + UT_R - 1) / UT_R, nc = (p + UT_C - 1) / UT_C;
+    int n = 0;
+    for (int I = 0; I < nr; ++I) n += nc - (I * UT_R) / UT_C;
+    return n;
+}
+
+template <int REG>
+__global__ void __launch_bounds__(UT_THREADS, 4)
+prox_mgl_upper_kernel(const double* __restrict__ Omega, const double* __restrict__ Omega_prev,
+                      double* __restrict__ X, double* __restrict__ Theta, const double* __restrict__ ctrl,
+                      double lambda1, double lambda2, int K, int p, double* __restrict__ partials)
+{
+    extern __shared__ double ysm[];                 // K * UT_THREADS
+    __shared__ double scratch[GG_NPART * 32];
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    // tile rows are grouped by UT_C / UT_R = 4: the rows of group g start at tile column g
+    const int nc = (p + UT_C - 1) / UT_C;
+    constexpr int GR = UT_C / UT_R;
+    int rem = blockIdx.x, g = 0;
+    while (rem >= GR * (nc - g)) { rem -= GR * (nc - g); ++g; }
+    const int I = g * GR + rem / (nc - g), J = g + rem % (nc - g);
+    const double inv_rho = 1.0 / ctrl[GG_C_RHO];
+    if (ctrl[GG_C_LAM1] > 0.0) { lambda1 = ctrl[GG_C_LAM1]; lambda2 = ctrl[GG_C_LAM2]; }
+    const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
+    const int i = I * UT_R + threadIdx.x / UT_C, j = J * UT_C + threadIdx.x % UT_C;
+    const size_t pp = (size_t)p * p;
+    const bool own = (i < p) && (j < p) && (i <= j);
+    double acc[GG_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (own) {
+        const size_t e = (size_t)i * p + j;
+        double* y = ysm + threadIdx.x;
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) y[k * UT_THREADS] = Omega[k * pp + e] + X[k * pp + e];
+        if (i != j) {
+            if (REG == 0) {            // GGL: group soft threshold of the l1-soft-thresholded vector
+                double ss = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    const double u = gg_soft(y[k * UT_THREADS], l1);
+                    y[k * UT_THREADS] = u;
+                    ss += u * u;
+                }
+                const double nrm = sqrt(ss);
+                const double a = nrm > l2 ? nrm : l2;
+                const double f = a - l2;
+                for (int k = 0; k < K; ++k) y[k * UT_THREADS] = (y[k * UT_THREADS] * f) / a;
+            } else {                   // FGL: TV prox across k, then l1 soft threshold
+                gg_tv1d_inplace(y, K, UT_THREADS, l2);
+                for (int k = 0; k < K; ++k) y[k * UT_THREADS] = gg_soft(y[k * UT_THREADS], l1);
+            }
+        }
+        const double w = (i == j) ? 1.0 : 2.0;      // an off-diagonal entry stands for itself and its mirror image
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * pp + e;
+            const double om = Omega[o], x = X[o], pv = Omega_prev[o];
+            const double th = y[k * UT_THREADS];
+            Theta[o] = th;
+            const double d1 = om - th;
+            const double xn = x + d1;               // X += Omega - Theta
+            X[o] = xn;
+            const double d2 = om - pv;
+            acc[0] += w * (om * om); acc[1] += w * (th * th); acc[2] += w * (xn * xn);
+            acc[3] += w * (d1 * d1); acc[4] += w * (d2 * d2);
+        }
+    }
+    gg_block_sum<GG_NPART>(acc, scratch);
+    if (threadIdx.x == 0) {
+        double* out = partials + (size_t)blockIdx.x * GG_NPART;
+#pragma unroll
+        for (int q = 0; q < GG_NPART; ++q) out[q] = acc[q];
+    }
+}
+
+// A[m][j][i] = A[m][i][j] for i < j, for two stacks at once (Theta and X after the upper-triangle loop).
+// One CTA per 32 x 32 tile pair (I <= J): coalesced read of tile (I,J), transposed through shared memory, coalesced
+// write of tile (J,I).
+__global__ void __launch_bounds__(256)
+mirror_upper_kernel(double* __restrict__ A0, double* __restrict__ A1, int p)
+{
+    __shared__ double t[32][33];
+    const int nt = (p + 31) / 32;
+    int rem = blockIdx.x, I = 0;
+    while (rem >= nt - I) { rem -= nt - I; ++I; }
+    const int J = I + rem;
+    double* A = (blockIdx.z ? A1 : A0) + (size_t)blockIdx.y * p * p;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = I * 32 + r, j = J * 32 + tx;
+        if (i < p && j < p) t[r][tx] = A[(size_t)i * p + j];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = J * 32 + r, j = I * 32 + tx;          // entry (i,j) of the mirror tile = t[tx][r]
+        if (i < p && j < p && i > j) A[(size_t)i * p + j] = t[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Stopping test + rho update, one CTA per problem; deterministic (fixed-order) reduction.
 __global__ void __launch_bounds__(256)
 stop_update_kernel(const double* __restrict__ partials, int nparts, double* __restrict__ ctrl,
@@ -792,6 +940,45 @@ int gg_launch_prox_mgl(const double* Omega, const double* Omega_prev, const doub
     }
     return latent ? launch_prox_mgl_t<1, true>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st)
                   : launch_prox_mgl_t<1, false>(Omega, Omega_prev, L, X, Theta, C, ctrl, l1, l2, K, p, partials, st);
+}
+
+extern "C" int gg_mgl_upper_nparts(int p) { return ut_ntiles(p); }
+
+int gg_launch_prox_mgl_upper(const double* Omega, const double* Omega_prev, double* X, double* Theta,
+                             const double* ctrl, double l1, double l2, int reg, int K, int p, double* partials,
+                             cudaStream_t st)
+{
+    const size_t smem = (size_t)K * UT_THREADS * sizeof(double);
+    if (smem > 200 * 1024) return -2;   // K too large for the shared-memory layout
+    auto kern = reg == 0 ? prox_mgl_upper_kernel<0> : prox_mgl_upper_kernel<1>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    gg_count_launch(1);
+    kern<<<ut_ntiles(p), UT_THREADS, smem, st>>>(Omega, Omega_prev, X, Theta, ctrl, l1, l2, K, p, partials);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_build_w_upper(const double* Theta, double* X, const double* S, const double* nk, const double* ctrl,
+                            int K, int p, double* W, cudaStream_t st)
+{
+    dim3 grid((p + 1) / 2, K);
+    gg_count_launch(1);
+    build_w_upper_kernel<<<grid, EW_THREADS, 0, st>>>(Theta, X, S, nk, ctrl, p, W);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_mirror_upper(double* A0, double* A1, int M, int p, cudaStream_t st)
+{
+    const int nt = (p + 31) / 32;
+    dim3 grid(nt * (nt + 1) / 2, M, A1 ? 2 : 1);
+    gg_count_launch(1);
+    mirror_upper_kernel<<<grid, 256, 0, st>>>(A0, A1, p);
+    GG_CHECK_LAUNCH();
+    return 0;
 }
 
 int gg_launch_stop_update(const double* partials, int nparts, double* ctrl, double* hist, int hist_cap,

@@ -42,6 +42,7 @@ struct TrWs {
     double* vbuf;    // (M,2,n)
     double* w;       // (M,TR_QMAX,n) ring of the w vectors of the pending (not yet written back) rank-2 updates
     double* y;       // (M,n)
+    int* cnt;        // (M) tile arrival counters of tr_step_kernel (zero between launches)
 #ifdef TR_TIMING
     long long* dbg;  // (n,2,8) time stamps of one CTA per launch (instrumented build only)
 #endif
@@ -87,23 +88,18 @@ __device__ __forceinline__ double tr_block_allsum(double v, double* scratch)
 // v_j.  The step sits on the critical path of the launch chain, so every independent global load (row j, y,
 // v_{j-1}) is issued up front into registers: the dependent chain is one memory round trip, two block reductions
 // (one barrier each) and the stores.   Element i = j + tid + e*blockDim.x, e < EPT.
-template <int EPT, int THR, bool PREF>
-__global__ void __launch_bounds__(THR)
-tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const int* __restrict__ skip)
+// (The body is shared by tr_col_kernel and by tr_step_kernel, where the CTA that finishes the last tile of a matrix
+//  runs it for the next column: row j and y are then data written by other CTAs of the SAME grid, hence the
+//  ld.global.cg loads -- L2 is the point of coherence, the fences are in tr_step_kernel.)
+template <int EPT, bool PREF>
+__device__ __forceinline__ void tr_col_body(const double* A, int n, int j, int kb, const TrWs& ws, int m, int sk,
+                                            bool stamp_on)
 {
     __shared__ double red1[32], red2[32];
     __shared__ double s_a1;
-    const int m = blockIdx.x;
 #ifdef TR_TIMING
-    const bool tr_stamp_on = (blockIdx.x == 0 && threadIdx.x == 0);
+    const bool tr_stamp_on = stamp_on;
 #endif
-    TR_STAMP(0, 0);
-    // Wait for the previous tr_symv_kernel first and only then release the next one: its CTAs start loading their
-    // tiles of A before their own wait, which is safe exactly because the last writer of A has completed here.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;");
-    TR_STAMP(0, 1);
-    const int sk = skip ? skip[m] : 0;        // consumed below, after the other loads have been issued
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* rowj = A + (size_t)m * n * n + (size_t)j * n;
     const double* vprev = ws.vbuf + ((size_t)m * 2 + ((j + 1) & 1)) * n;    // v^{(j-1)}
@@ -119,12 +115,12 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
     for (int e = 0; e < EPT; ++e) {
         const int i = j + tid + e * nt;
         const bool ok = i < n;
-        a[e] = ok ? rowj[i] : 0.0;
-        yv[e] = (ok && j >= 1) ? y[i] : 0.0;
+        a[e] = ok ? __ldcg(rowj + i) : 0.0;
+        yv[e] = (ok && j >= 1) ? __ldcg(y + i) : 0.0;
         vp[e] = (ok && j >= 1) ? vprev[i] : 0.0;
     }
     double tp = 0.0, yj = 0.0;
-    if (j >= 1) { tp = tau[j - 1]; yj = y[j]; }
+    if (j >= 1) { tp = tau[j - 1]; yj = __ldcg(y + j); }
     // older pending pairs kb..j-2 (independent of w_{j-1}): a_i -= v_k[i] w_k[j] + w_k[i] v_k[j]
     // (PREF: fully unrolled with predicates so that all of these loads are in flight together with the ones above;
     //  the large-p variant keeps them in a loop -- no register spills in any kernel of the launch chain)
@@ -222,6 +218,24 @@ tr_col_kernel(const double* __restrict__ A, int n, int j, int kb, TrWs ws, const
     TR_STAMP(0, 5);
 }
 
+template <int EPT, int THR, bool PREF>
+__global__ void __launch_bounds__(THR)
+tr_col_kernel(const double* A, int n, int j, int kb, TrWs ws, const int* __restrict__ skip)
+{
+    const int m = blockIdx.x;
+#ifdef TR_TIMING
+    const bool tr_stamp_on = (blockIdx.x == 0 && threadIdx.x == 0);
+#endif
+    TR_STAMP(0, 0);
+    // Wait for the previous tr_symv_kernel first and only then release the next one: its CTAs start loading their
+    // tiles of A before their own wait, which is safe exactly because the last writer of A has completed here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    TR_STAMP(0, 1);
+    const int sk = skip ? skip[m] : 0;        // consumed in the body, after the other loads have been issued
+    tr_col_body<EPT, PREF>(A, n, j, kb, ws, m, sk, blockIdx.x == 0 && threadIdx.x == 0);
+}
+
 // Streams the UPPER triangle of the trailing block, one CTA per 64x64 tile (I <= J): applies the pending rank-2
 // updates kb..j-1 (a_rc -= v_k[r] w_k[c] + w_k[r] v_k[c]) in registers, stores the tile only on a write pass, and
 // accumulates the full symmetric y = A v from that single pass: y_I += T v_J (row sums) and, mirrored,
@@ -262,8 +276,10 @@ __device__ __forceinline__ void sv_st(double* p, double v, int hint, unsigned lo
 
 template <bool INTERIOR>
 __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int j, int kb, int write, const TrWs& ws,
-                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm, int r_pin)
+                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm, int r_pin,
+                                             int pdl, bool& skipped)
 {
+    skipped = true;
     const int t = n - j - 1, base = j + 1, cnt = j - kb;
 #ifdef TR_TIMING
     const bool tr_stamp_on = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
@@ -276,6 +292,13 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
     // The tile is loaded BEFORE griddepcontrol.wait: A is written only by tr_symv_kernel launches, and the previous
     // one had completed before the column kernel in between released this grid (see tr_col_kernel), so these loads
     // overlap the column step.  ld.global.cg: straight from L2 -- no reuse, and no stale L1 lines across launches.
+    // pdl 0 (tr_symv_kernel): as described above.  tr_step_kernel has no column kernel in between, so its grids wait
+    // for their predecessor and only then release their successor (whose CTAs therefore never run beside a grid
+    // older than their predecessor); pdl 1: the predecessor did not store A -- load early; pdl 2: it did -- wait first.
+    if (pdl == 2) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
     double a[4][4];
     unsigned okm = 0xffffu;
     const int hint = r_pin >= 0;
@@ -301,7 +324,8 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
                 a[i][jj] = ok ? sv_ld(pt + (size_t)i * n + 16 * jj, hint, pol) : 0.0;
             }
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything below reads what the column kernel wrote
+    if (pdl != 2) asm volatile("griddepcontrol.wait;" ::: "memory");   // everything below reads what the column step wrote
+    if (pdl == 1) asm volatile("griddepcontrol.launch_dependents;");
     TR_STAMP(1, 1);
     const int sk = skip ? skip[m] : 0;
     const double* vcur = ws.vbuf + ((size_t)m * 2 + (j & 1)) * n + base;
@@ -322,6 +346,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
         cv = (INTERIOR || pos < t) ? vcur[pos] : 0.0;
     }
     if (sk) return;                           // (block-uniform; no barrier has been passed yet)
+    skipped = false;
     TR_STAMP(1, 2);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -434,8 +459,50 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
     TR_STAMP(1, 0);
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
-    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin);
-    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin);
+    bool skipped;
+    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, 0, skipped);
+    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, 0, skipped);
+}
+
+// tr_symv_kernel(j) followed, in the same launch, by the column step j+1 (tr_col_body): the CTA that finishes the last
+// tile of a matrix -- found with a per-matrix arrival counter -- runs it, so a column costs ONE launch boundary instead
+// of two and the column steps of all matrices but the last to finish are hidden behind the tile work of the others.
+// Ordering: every thread fences its atomics on y / stores of A before the CTA's arrival; the last CTA fences again
+// before it reads y and row j+1 (ld.global.cg).  col_next = 0 on the last chain step (tr_tail_kernel continues).
+__global__ void __launch_bounds__(256, 3)
+tr_step_kernel(double* A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt, int r_pin,
+               int early, int col_next)
+{
+    __shared__ SvSmem sm;
+    __shared__ int s_last;
+    const bool rev = (j & 1) != 0;
+    const int m = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    int idx = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, I = 0;
+    while (idx >= nt - I) { idx -= nt - I; ++I; }
+    const int J = I + idx;
+#ifdef TR_TIMING
+    const bool tr_stamp_on = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+#endif
+    TR_STAMP(1, 0);
+    const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
+    bool skipped;
+    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, early ? 1 : 2, skipped);
+    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, early ? 1 : 2, skipped);
+    if (skipped || !col_next) return;         // (block-uniform)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // release (cumulative over the CTA's atomics and stores, ordered by the barrier) / acquire in one RMW
+        int prev;
+        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(prev) : "l"(ws.cnt + m) : "memory");
+        s_last = (prev == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) ws.cnt[m] = 0;
+    const int jn = j + 1, kbn = write ? j : kb, len = n - jn;
+    if (len <= 512) tr_col_body<2, true>(A, n, jn, kbn, ws, m, 0, false);
+    else if (len <= 1024) tr_col_body<4, false>(A, n, jn, kbn, ws, m, 0, false);
+    else tr_col_body<8, false>(A, n, jn, kbn, ws, m, 0, false);
 }
 
 // Tail of the tridiagonalisation: once the trailing block has at most TR_TAIL rows it fits in shared memory, and
@@ -1565,7 +1632,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += al(sizeof(int) * (size_t)M * (1 << L) * 2) + 2 * al(sizeof(int) * Mn);   // nodeka, lista, listb
     b += al(sizeof(double) * (size_t)M * (1 << L));       // noderho
     b += al(sizeof(double) * (size_t)M * npanels * BT_NB * BT_NB);
-    b += al(sizeof(int) * (size_t)M);                     // skip
+    b += 2 * al(sizeof(int) * (size_t)M);                 // skip, cnt
     b += al(sizeof(double) * (size_t)M);                  // scale
     b += 2 * al(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);   // G, X of the blocked back-transformation
     if (n >= BB_MIN) b += al(sizeof(double) * M * nn);   // V' = X V
@@ -1613,6 +1680,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     dw.listb = (int*)take(sizeof(int) * Mn);
     double* Tm = (double*)take(sizeof(double) * (size_t)M * (npanels + 1) * BT_NB * BT_NB);
     int* skip = (int*)take(sizeof(int) * (size_t)M);
+    tw.cnt = (int*)take(sizeof(int) * (size_t)M);
     double* scale = (double*)take(sizeof(double) * (size_t)M);
     const int npb = (n - 1 + BB_NB - 1) / BB_NB;
     double* Gb = (double*)take(sizeof(double) * (size_t)M * ((n + BB_NB - 1) / BB_NB) * BB_NB * BB_NB);
@@ -1697,7 +1765,42 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         }
         const int lazy_q = gg_tr_lazy_depth();
         int kb = jb;                                  // pairs kb..j-1 are pending at step j
-        for (int j = jb; j < js && chain; ++j) {
+        // merged chain (GG_TR_MERGE=1, n - jb <= 2048): column step jb alone, then one tr_step_kernel per column.
+        // Measured on B200 (profiles/r02_chain_merge.json) it is SLOWER than the two-launch chain at every shape
+        // (K=20 p=1000: 13.4 vs 12.0 ms, K=3: 6.1 vs 5.7, K=10 p=500: 2.85 vs 2.58): the arrival counter + acquire +
+        // re-read of y through L2 costs more than a programmatic-dependent-launch boundary, and the grid after a
+        // write pass loses its early tile loads.  Kept as an option, not the default.
+        const int tr_merge = sytrd_blocked_env("GG_TR_MERGE", 0);
+        const bool merged = tr_merge && chain && !prof12 && (n - jb) <= 2048 && js > jb && js < n;
+        if (merged) {
+            if (cudaMemsetAsync(tw.cnt, 0, sizeof(int) * (size_t)M, s) != cudaSuccess) return -6;
+            int prev_write = 1;                       // (nothing is in flight before the first step: either is safe)
+            for (int j = jb; j < js; ++j) {
+                if (j == jb) {
+                    const int len = n - j;
+                    cfg.gridDim = dim3(M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+                    cudaError_t e;
+                    gg_count_launch(1);
+                    if (len <= 512) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<2, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                    else if (len <= 1024) e = cudaLaunchKernelEx(&cfg, tr_col_kernel<4, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                    else e = cudaLaunchKernelEx(&cfg, tr_col_kernel<8, 256, true>, (const double*)A, n, j, kb, tw, (const int*)skip);
+                    if (e != cudaSuccess) return (int)e;
+                }
+                const int write = (j - kb >= lazy_q || (j == js - 1 && j > kb)) ? 1 : 0;
+                const int t = n - j - 1;
+                const int nt = (t + SV_T - 1) / SV_T;
+                cfg.gridDim = dim3(nt * (nt + 1) / 2, M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+                gg_count_launch(1);
+                // the grid after the standalone column kernel must not load early either: that kernel releases its
+                // dependents after ITS wait, but the grid before it may be a blocked-path kernel without the protocol
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_step_kernel, A, n, j, kb, write, tw, (const int*)skip, nt, r_pin,
+                                                   (prev_write || j == jb) ? 0 : 1, (j + 1 < js) ? 1 : 0);
+                if (e != cudaSuccess) return (int)e;
+                prev_write = write;
+                if (write) kb = j;
+            }
+        }
+        for (int j = jb; j < js && chain && !merged; ++j) {
             if (which != 2) {
                 const int len = n - j;
                 const int thr = len <= 2048 ? 256 : 512;

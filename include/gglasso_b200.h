@@ -111,6 +111,19 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
                 double* C, const double* ctrl, double lambda1, double lambda2, int reg, int K, int p,
                 double* partials, void* stream);
 
+/* The same prox + dual update + residual sums on the UPPER triangles only (non-latent loop; 2.5 A bytes instead of
+ * 5 A): Theta and X are written for i <= j, the residual sums count off-diagonal entries twice.  The consumers inside
+ * the loop (gg_build_w_upper, the tridiagonal path of gg_eigh) read upper triangles only; gg_mirror_upper fills the
+ * lower triangles of up to two (M,p,p) stacks afterwards -- the mirroring of prox_p (ggl_helper.py:198-205) done once
+ * instead of every iteration.  partials: gg_mgl_upper_nparts(p) * GG_NPART doubles.
+ * gg_build_w_upper: W = Theta - X - (n_k/rho) S for i <= j (admm_solver.py:180), one problem of K instances. */
+int gg_mgl_upper_nparts(int p);
+int gg_prox_mgl_upper(const double* Omega, const double* Omega_prev, double* X, double* Theta, const double* ctrl,
+                      double lambda1, double lambda2, int reg, int K, int p, double* partials, void* stream);
+int gg_build_w_upper(const double* Theta, double* X, const double* S, const double* nk, const double* ctrl, int K,
+                     int p, double* W, void* stream);
+int gg_mirror_upper(double* A0, double* A1, int M, int p, void* stream);
+
 /* K-sharded MGL (one process per GPU): V = (Omega + L) + X on the local instances
  * (L may be NULL), and the cross-instance prox on a row band: V, Theta are (K, nb, p) slabs holding global rows
  * row0..row0+nb-1 of all K instances (after the all-to-all re-tile).  Same prox as gg_prox_mgl. */

@@ -179,6 +179,79 @@ def test_prox_mgl_fused_dual_and_norms(reg, K, p):
     np.testing.assert_allclose(sums, ref, rtol=1e-12)
 
 
+@pytest.mark.parametrize("reg,K,p", [("GGL", 2, 16), ("FGL", 5, 33), ("GGL", 20, 70), ("FGL", 20, 257), ("FGL", 31, 17),
+                                      ("GGL", 3, 1), ("FGL", 7, 100)])
+def test_prox_mgl_upper_triangle_kernels(reg, K, p):
+    """the upper-triangle loop kernels (gg_prox_mgl_upper, gg_build_w_upper) followed by gg_mirror_upper give the same
+    Theta, X and residual sums as the oracle's prox_p + dual update on full matrices; the lower triangles are not
+    touched before the mirror pass"""
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import to_dev, _p
+    from oracle import admm_oracle as orc
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(K * 1000 + p)
+    Om, Omp, X, S = (np.stack([_sym(rng, p, 0.3) for _ in range(K)]) for _ in range(4))
+    rho, l1, l2 = 2.0, 0.21, 0.13
+    want = orc.prox_p(Om + X, l1 / rho, l2 / rho, reg)
+    Xn = X + (Om - want)
+    n = lib.gg_mgl_upper_nparts(p)
+    parts = torch.zeros((n, 5), dtype=torch.float64, device=dev)
+    dOm, dOmp, dX, dS = to_dev(Om, dev), to_dev(Omp, dev), to_dev(X, dev), to_dev(S, dev)
+    Th = torch.full_like(dOm, 7.0)
+    ctrl = _ctrl(dev, rho)
+    rc = lib.gg_prox_mgl_upper(_p(dOm), _p(dOmp), _p(dX), _p(Th), _p(ctrl), l1, l2, 0 if reg == "GGL" else 1, K, p,
+                               _p(parts), 0)
+    assert rc == 0
+    iu = np.triu_indices(p)
+    il = np.tril_indices(p, -1)
+    got, gotX = Th.cpu().numpy(), dX.cpu().numpy()
+    assert np.abs(got[:, iu[0], iu[1]] - want[:, iu[0], iu[1]]).max() < 1e-15
+    assert np.all(got[:, il[0], il[1]] == 7.0)                       # lower triangle untouched
+    assert np.array_equal(gotX[:, il[0], il[1]], X[:, il[0], il[1]])
+    sums = parts.sum(0).cpu().numpy()
+    ref = [np.sum(Om ** 2), np.sum(want ** 2), np.sum(Xn ** 2), np.sum((Om - want) ** 2), np.sum((Om - Omp) ** 2)]
+    np.testing.assert_allclose(sums, ref, rtol=1e-12)
+    # W on the upper triangle, with a pending X rescale
+    ctrl[0, 1] = 0.5
+    nk = to_dev(np.arange(1, K + 1, dtype=np.float64), dev)
+    W = torch.full_like(dOm, -3.0)
+    Xb = dX.clone()
+    assert lib.gg_build_w_upper(_p(Th), _p(Xb), _p(dS), _p(nk), _p(ctrl), K, p, _p(W), 0) == 0
+    Wg = W.cpu().numpy()
+    Wref = got - 0.5 * gotX - (np.arange(1, K + 1)[:, None, None] / rho) * S
+    assert np.abs(Wg[:, iu[0], iu[1]] - Wref[:, iu[0], iu[1]]).max() < 1e-14
+    assert np.all(Wg[:, il[0], il[1]] == -3.0)
+    assert np.array_equal(Xb.cpu().numpy()[:, iu[0], iu[1]], 0.5 * gotX[:, iu[0], iu[1]])
+    # mirror pass
+    assert lib.gg_mirror_upper(_p(Th), _p(dX), K, p, 0) == 0
+    got, gotX = Th.cpu().numpy(), dX.cpu().numpy()
+    assert np.array_equal(got, got.transpose(0, 2, 1)) and np.array_equal(gotX, gotX.transpose(0, 2, 1))
+    assert np.abs(got - want).max() < 1e-15 and np.array_equal(got != 0, want != 0)
+    assert np.abs(gotX - Xn).max() < 1e-15
+
+
+@pytest.mark.parametrize("reg,K,p", [("GGL", 4, 120), ("FGL", 5, 97)])
+def test_upper_triangle_loop_equals_full_loop(reg, K, p, monkeypatch):
+    """ADMM_MGL with the upper-triangle iteration (default for the tridiagonal eigensolver path) and with the
+    full-matrix kernels (GG_UPPER=0): same iteration count, same solution"""
+    import gglasso_b200
+    rng = np.random.default_rng(p)
+    S = np.stack([np.cov(rng.standard_normal((p, 3 * p)), bias=True) for _ in range(K)])
+    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    sols = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GG_UPPER", flag)
+        sol, info = gglasso_b200.ADMM_MGL(S, 0.1, 0.05, reg, Om0, tol=1e-8, rtol=1e-8, verbose=False)
+        sols.append((sol, info))
+    (a, ia), (b, ib) = sols
+    assert ia["status"] == ib["status"] == "optimal"
+    for k in ("Omega", "Theta", "X"):
+        assert np.abs(a[k] - b[k]).max() < 1e-11, k
+        assert np.array_equal(a[k], a[k].transpose(0, 2, 1))
+    assert np.array_equal(a["Theta"] != 0, b["Theta"] != 0)
+
+
 @pytest.mark.parametrize("p,masked", [(1, False), (7, False), (100, True), (257, False)])
 def test_prox_sgl_kernel(p, masked):
     from gglasso_b200 import _lib
