@@ -88,6 +88,20 @@ def test_eigh_clustered_and_scaled():
             assert _rel((V * f) @ V.T, ref) < 1e-10
 
 
+@pytest.mark.parametrize("M,p", [(3, 300), (1, 777)])
+def test_eigh_merged_chain_option(M, p, monkeypatch):
+    """GG_TR_MERGE=1: one launch per column (the CTA finishing a matrix's last tile runs the next column step)"""
+    from gglasso_b200._engine import eigh
+    monkeypatch.setenv("GG_TR_MERGE", "1")
+    rng = np.random.default_rng(p)
+    A = np.stack([_sym(rng, p) for _ in range(M)])
+    D, Q = eigh(A)
+    assert np.abs(D - np.linalg.eigvalsh(A)).max() < 1e-11
+    for m in range(M):
+        assert np.abs(Q[m].T @ Q[m] - np.eye(p)).max() < 1e-12
+        assert np.abs(A[m] @ Q[m] - Q[m] * D[m]).max() < 1e-11
+
+
 @pytest.mark.parametrize("p", [5, 64, 100, 161, 257, 384])
 def test_recon_modes(p):
     from gglasso_b200 import _lib
