@@ -140,3 +140,21 @@ def test_non_finite_input_raises_instead_of_iterating():
     S3[1, 0, 1] = S3[1, 1, 0] = np.inf
     with pytest.raises((GGLassoB200Error, AssertionError)):
         _quiet(ADMM_MGL, S3, 0.1, 0.1, "GGL", np.repeat(np.eye(p)[None], 2, 0), max_iter=50)
+
+
+def test_upload_from_pinned_and_pageable_host_arrays_agree():
+    """to_dev: page-locked caller arrays take the single-DMA path, pageable ones the threaded staging path"""
+    import torch
+    from gglasso_b200._engine import to_dev, require_cuda
+    dev = require_cuda()
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((3, 700, 700))                       # 11.8 MB: above the staging threshold
+    h = torch.empty(a.shape, dtype=torch.float64, pin_memory=True).numpy()
+    h[...] = a
+    assert torch.from_numpy(h).is_pinned() and not torch.from_numpy(a).is_pinned()
+    d1, d2 = to_dev(a, dev), to_dev(h, dev)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2) and np.array_equal(d1.cpu().numpy(), a)
+    hp = torch.empty((60, 60), dtype=torch.float64, pin_memory=True).numpy()        # small arrays: plain path
+    hp[...] = np.eye(60)
+    assert np.array_equal(to_dev(hp, dev).cpu().numpy(), np.eye(60))
