@@ -634,6 +634,8 @@ struct DcWs {
     int* nodeka;      // (M,nodes_max,2) lengths of the two per-child K lists below
     int* lista;       // (M,n) non-deflated poles whose row of Qt has entries in the first child's columns
     int* listb;       // (M,n) ... in the second child's columns (rows mixed by a Givens deflation are in both)
+    int* dfl;         // (M,n) deflated rows of every node, in output order (read by dc_copy_deflated_kernel)
+    int* nodendf;     // (M,nodes_max) their number
     double* noderho;  // (M,nodes_max)
     double* U;        // (M,n,n) Delta / eigenvector matrices, block diagonal like Qt
     int nodes_max;
@@ -759,8 +761,42 @@ dc_leaf_kernel(const double* __restrict__ d, const double* __restrict__ e, int n
     }
 }
 
-// One CTA per node: z vector, sort, deflation (serial scan by thread 0), Givens rotations on rows,
-// copies of deflated rows/eigenvalues to the output buffers.
+// exclusive prefix sum of one int per thread over the block (<= 1024 threads); total in *tot.  scratch: 33 ints
+__device__ __forceinline__ int dc_block_excl_scan(int v, int* scratch, int* tot)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) scratch[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? scratch[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        scratch[lane] = wi - w;                  // exclusive offset of warp `lane`
+        if (lane == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    const int res = scratch[wid] + incl - v;
+    *tot = scratch[32];
+    __syncthreads();                             // scratch may be reused by the caller
+    return res;
+}
+
+// One CTA per node: z vector, sort, deflation, Givens rotations on rows, eigenvalues of the deflated pairs.
+// Deflation runs in parallel under the assumption that no two poles are close enough to be rotated into each
+// other (dlaed2's second criterion): small z components are flagged, the survivors compacted with block scans, every
+// neighbouring pair of survivors is tested, and only if a pair fails the test thread 0 redoes the merge with the
+// serial scan (identical results by construction: without a rotation the serial scan produces exactly these lists).
+// The deflated rows are copied by dc_copy_deflated_kernel (many CTAs) instead of this one-CTA-per-node kernel.
 __global__ void __launch_bounds__(1024)
 dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* __restrict__ lam_in,
                   double* __restrict__ lam_out, double* __restrict__ Qin, double* __restrict__ Qout, DcWs ws,
@@ -786,7 +822,6 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
     __shared__ double s_rho, s_red[64], s_max[2];
     const int tid = threadIdx.x, nt = blockDim.x;
     double* Qm = Qin + (size_t)m * n * n;
-    double* Qo = Qout + (size_t)m * n * n;
     const double es = e[(size_t)m * n + mid - 1];
     const double sgn = es >= 0.0 ? 1.0 : -1.0;
     const double rho = 2.0 * fabs(es);
@@ -817,7 +852,61 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
         if (tid == 0) { s_max[0] = dm; s_max[1] = zm; }
     }
     __syncthreads();
-    if (tid == 0) {
+    __shared__ int s_scan[33];
+    int* la = ws.lista + (size_t)m * n + lo;
+    int* lb = ws.listb + (size_t)m * n + lo;
+    bool serial = true;
+    {
+        const double dmax = s_max[0], zmax = s_max[1];
+        const double tol = 8.0 * TR_EPS * fmax(dmax, zmax);
+        if (!(rho * zmax <= tol)) {
+            const int C = (N + nt - 1) / nt;
+            const int t0 = min(N, tid * C), t1 = min(N, t0 + C);
+            int cs = 0;
+            for (int t = t0; t < t1; ++t) cs += (rho * fabs(sz[idx[t]]) <= tol) ? 1 : 0;
+            int ndf_p;
+            const int off = dc_block_excl_scan(cs, s_scan, &ndf_p);
+            int sp = off, cp = t0 - off;
+            for (int t = t0; t < t1; ++t) {
+                const int nj = idx[t];
+                if (rho * fabs(sz[nj]) <= tol) df[sp++] = nj;
+                else nd[cp++] = nj;
+            }
+            __syncthreads();
+            const int k_p = N - ndf_p;
+            int trig = 0;
+            for (int c = tid + 1; c < k_p; c += nt) {
+                const int pj = nd[c - 1], nj = nd[c];
+                const double sv = sz[pj], cv = sz[nj];
+                const double den = cv * cv + sv * sv;
+                const double tt = sd[nj] - sd[pj];
+                trig |= (fabs(tt * cv * sv) <= tol * den) ? 1 : 0;
+            }
+            if (!__syncthreads_or(trig)) {
+                serial = false;
+                // K lists of the two children (no rotation: every pole belongs to exactly one child)
+                const int C2 = (k_p + nt - 1) / nt;
+                const int c0 = min(k_p, tid * C2), c1 = min(k_p, c0 + C2);
+                int ca = 0;
+                for (int c = c0; c < c1; ++c) ca += (typ[nd[c]] != 3) ? 1 : 0;
+                int ka_p;
+                const int offa = dc_block_excl_scan(ca, s_scan, &ka_p);
+                int pa = offa, pb = c0 - offa;
+                for (int c = c0; c < c1; ++c) {
+                    if (typ[nd[c]] != 3) la[pa++] = c;
+                    else lb[pb++] = c;
+                }
+                if (tid == 0) {
+                    ws.nodeka[((size_t)m * ws.nodes_max + node) * 2] = ka_p;
+                    ws.nodeka[((size_t)m * ws.nodes_max + node) * 2 + 1] = k_p - ka_p;
+                    s_k = k_p; s_ndf = ndf_p; s_nrot = 0; s_rho = rho;
+                    ws.nodek[(size_t)m * ws.nodes_max + node] = k_p;
+                    ws.noderho[(size_t)m * ws.nodes_max + node] = rho;
+                }
+            }
+        }
+    }
+    if (serial && tid == 0) {
         const double dmax = s_max[0], zmax = s_max[1];
         const double tol = 8.0 * TR_EPS * fmax(dmax, zmax);
         int k = 0, ndf = 0, nrot = 0, pj = -1;
@@ -855,8 +944,6 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
         // The rows of Qt are block diagonal (each child's eigenvectors live in its own columns), so the basis update
         // of a column range only needs the poles whose row has entries there: two K lists, as dlaed3's coltyp split
         int ka = 0, kb = 0;
-        int* la = ws.lista + (size_t)m * n + lo;
-        int* lb = ws.listb + (size_t)m * n + lo;
         for (int i = 0; i < k; ++i) {
             const int ty = typ[nd[i]];
             if (ty != 3) la[ka++] = i;
@@ -888,21 +975,38 @@ dc_prepare_kernel(const double* __restrict__ e, int n, int level, const double* 
         ws.dl[(size_t)m * n + lo + i] = sd[nd[i]];
         ws.wnd[(size_t)m * n + lo + i] = sz[nd[i]];
     }
-    // deflated eigenpairs go to rows lo+k.. of the output unchanged
-    // (one warp per row, four independent loads in flight per lane: the rows are independent copies)
-    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    for (int t = wid; t < ndf; t += nw) {
-        const double* src = Qm + (size_t)(lo + df[t]) * n + lo;
-        double* dst = Qo + (size_t)(lo + k + t) * n + lo;
-        for (int col = lane; col < N; col += 128) {
-            double v[4];
+    // deflated eigenpairs go to rows lo+k.. of the output unchanged: eigenvalues here, rows in dc_copy_deflated_kernel
+    int* dfl = ws.dfl + (size_t)m * n + lo;
+    for (int t = tid; t < ndf; t += nt) {
+        dfl[t] = df[t];
+        lam_out[(size_t)m * n + lo + k + t] = sd[df[t]];
+    }
+    if (tid == 0) ws.nodendf[(size_t)m * ws.nodes_max + node] = ndf;
+}
+
+// Qout[lo+k+t][lo..hi) = Qin[lo+dfl[t]][lo..hi): one warp per deflated row.  grid (ceil(Nmax/8), nodes, M)
+__global__ void __launch_bounds__(256)
+dc_copy_deflated_kernel(int n, int level, const double* __restrict__ Qin, double* __restrict__ Qout, DcWs ws,
+                        const int* __restrict__ skip)
+{
+    const int m = blockIdx.z;
+    if (skip && skip[m]) return;
+    const int node = blockIdx.y;
+    const int ndf = ws.nodendf[(size_t)m * ws.nodes_max + node];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x * 8 + wid;
+    if (t >= ndf) return;
+    const int k = ws.nodek[(size_t)m * ws.nodes_max + node];
+    const int lo = dc_bnd(n, level, node), N = dc_bnd(n, level, node + 1) - lo;
+    const double* src = Qin + (size_t)m * n * n + (size_t)(lo + ws.dfl[(size_t)m * n + lo + t]) * n + lo;
+    double* dst = Qout + (size_t)m * n * n + (size_t)(lo + k + t) * n + lo;
+    for (int col = lane; col < N; col += 128) {
+        double v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (col + 32 * u < N) ? src[col + 32 * u] : 0.0;
+        for (int u = 0; u < 4; ++u) v[u] = (col + 32 * u < N) ? src[col + 32 * u] : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (col + 32 * u < N) dst[col + 32 * u] = v[u];
-        }
-        if (lane == 0) lam_out[(size_t)m * n + lo + k + t] = sd[df[t]];
+        for (int u = 0; u < 4; ++u)
+            if (col + 32 * u < N) dst[col + 32 * u] = v[u];
     }
 }
 
@@ -1630,6 +1734,7 @@ size_t gg_tridiag_ws_bytes(int M, int n)
     b += 3 * al(sizeof(int) * Mn) + 2 * al(sizeof(double) * Mn);   // ndrow, rotp, rotn, rotc, rots
     b += al(sizeof(int) * (size_t)M * (1 << L));          // nodek
     b += al(sizeof(int) * (size_t)M * (1 << L) * 2) + 2 * al(sizeof(int) * Mn);   // nodeka, lista, listb
+    b += al(sizeof(int) * Mn) + al(sizeof(int) * (size_t)M * (1 << L));           // dfl, nodendf
     b += al(sizeof(double) * (size_t)M * (1 << L));       // noderho
     b += al(sizeof(double) * (size_t)M * npanels * BT_NB * BT_NB);
     b += 2 * al(sizeof(int) * (size_t)M);                 // skip, cnt
@@ -1678,6 +1783,8 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     dw.nodeka = (int*)take(sizeof(int) * (size_t)M * dw.nodes_max * 2);
     dw.lista = (int*)take(sizeof(int) * Mn);
     dw.listb = (int*)take(sizeof(int) * Mn);
+    dw.dfl = (int*)take(sizeof(int) * Mn);
+    dw.nodendf = (int*)take(sizeof(int) * (size_t)M * dw.nodes_max);
     double* Tm = (double*)take(sizeof(double) * (size_t)M * (npanels + 1) * BT_NB * BT_NB);
     int* skip = (int*)take(sizeof(int) * (size_t)M);
     tw.cnt = (int*)take(sizeof(int) * (size_t)M);
@@ -1900,6 +2007,8 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         gg_count_launch(1);
         dc_prepare_kernel<<<dim3(nodes, M), 1024, psm, s>>>(tw.e, n, l, dw.lam[(l + 1) & 1], dw.lam[l & 1],
                                                             (double*)Qin, Qout, dw, skip);
+        gg_count_launch(1);
+        dc_copy_deflated_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, 0, s>>>(n, l, Qin, Qout, dw, skip);
         gg_count_launch(1);
         dc_secular_kernel<<<dim3((Nmax + 7) / 8, nodes, M), 256, sizeof(double) * 2 * Nmax, s>>>(n, l, dw.lam[l & 1], dw, skip);
         gg_count_launch(1);
