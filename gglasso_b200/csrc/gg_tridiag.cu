@@ -1577,23 +1577,33 @@ bb_gram_kernel(const double* __restrict__ Vh, int n, int npb, double* __restrict
 
 // X_P (lower triangular, = T^T of the block): rows are independent; eight lanes share a row (they split the dot
 // product of every recurrence step), four rows per warp.  grid (npb, M), 8 * BB_NB threads
+// The strictly lower triangle of G is staged in shared memory first (packed rows, 65 KB): the 127 steps of the
+// recurrence are strictly dependent, and reading G from global memory put an L2 round trip into every one of them
+// (0.22 ms per eigh at K=20, p=1000 for 20 KFLOP of work per row).
+#define BB_GTRI (BB_NB * (BB_NB - 1) / 2)
+__device__ __forceinline__ int bb_goff(int i) { return i * (BB_NB - 1) - i * (i - 1) / 2; }   // row i: q = i+1..127
 __global__ void __launch_bounds__(8 * BB_NB)
 bb_x_kernel(const double* __restrict__ G, const double* __restrict__ tau, int n, int npb, double* __restrict__ X,
             const int* __restrict__ skip)
 {
-    extern __shared__ double xs[];                   // [BB_NB][BB_NB + 1]
+    extern __shared__ double xs[];                   // [BB_NB][BB_NB + 1], then gs[BB_GTRI]
+    double* gs = xs + BB_NB * (BB_NB + 1);
     const int m = blockIdx.y, P = blockIdx.x;
     if (skip && skip[m]) return;
     const int j0 = P * BB_NB, a = threadIdx.x >> 3, l = threadIdx.x & 7;
     const int amax = a | 3;                          // last row handled by this warp
     const double* Gp = G + ((size_t)m * npb + P) * BB_NB * BB_NB;
     const double* tp = tau + (size_t)m * n + j0;
+    for (int idx = threadIdx.x; idx < BB_NB * BB_NB; idx += 8 * BB_NB) {
+        const int i = idx / BB_NB, q = idx % BB_NB;  // G is symmetric: row i, contiguous in q
+        if (q > i) gs[bb_goff(i) + q - i - 1] = Gp[idx];
+    }
     double* xr = xs + (size_t)a * (BB_NB + 1);
     for (int i = a + 1 + l; i < BB_NB; i += 8) xr[i] = 0.0;
     if (l == 0) xr[a] = (j0 + a < n - 1) ? tp[a] : 0.0;
-    __syncwarp();
+    __syncthreads();
     for (int i = amax - 1; i >= 0; --i) {
-        const double* gi = Gp + (size_t)i * BB_NB;   // G is symmetric: row i, contiguous in q
+        const double* gi = gs + bb_goff(i) - i - 1;  // gi[q] = G[i][q], q > i
         double sacc = 0.0;
         if (i < a)
             for (int q = i + 1 + l; q <= a; q += 8) sacc = fma(xr[q], gi[q], sacc);
@@ -1964,14 +1974,14 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
         bt_big = ev ? atoi(ev) : 1;
     }
     cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                  // (per device)
-                         (int)(sizeof(double) * BB_NB * (BB_NB + 1)));
+                         (int)(sizeof(double) * (BB_NB * (BB_NB + 1) + BB_GTRI)));
     const bool use_big = npanels > 0 && which != 4 && bt_big && n >= BB_MIN;
     if (use_big) {
         const int nt64 = (n + BB_T - 1) / BB_T;
         gg_count_launch(1);
         bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, n, npb, Gb, skip);
         gg_count_launch(1);
-        bb_x_kernel<<<dim3(npb, M), 8 * BB_NB, sizeof(double) * BB_NB * (BB_NB + 1), s>>>(Gb, tw.tau, n, npb, Xb, skip);
+        bb_x_kernel<<<dim3(npb, M), 8 * BB_NB, sizeof(double) * (BB_NB * (BB_NB + 1) + BB_GTRI), s>>>(Gb, tw.tau, n, npb, Xb, skip);
         gg_count_launch(1);
         bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, Xb, n, npb, Vp, skip);
         GG_CHECK_LAUNCH();
