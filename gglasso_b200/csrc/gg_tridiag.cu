@@ -1965,9 +1965,10 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     if (stop_after == 1 || (which != 0 && which != 4)) return 0;
 
     // ---- stage 3 preparation: G, X, V' of the blocked back-transformation (independent of stage 2).
-    // (Running these three launches on a side stream next to the divide & conquer kernels gained 0.3 ms at cfg3 but
-    // corrupted results when five host threads drove five solves concurrently -- see DESIGN.md 4.4; they are plain
-    // launches on the caller's stream.)
+    // (Round 1: running these three launches on a side stream next to the divide & conquer kernels gained 0.3 ms at
+    // cfg3 but corrupted results when five host threads drove five solves concurrently -- DESIGN.md 4.4.  The
+    // GG_BT_SIDE=1 variant below shares nothing between threads and passed the concurrent-solve stress test, but
+    // since the round-1 failure was never explained the default stays: plain launches on the caller's stream.)
     static int bt_big = -1;
     if (bt_big < 0) {
         const char* ev = getenv("GG_BT_BIG");
@@ -1976,15 +1977,38 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     cudaFuncSetAttribute(bb_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                  // (per device)
                          (int)(sizeof(double) * (BB_NB * (BB_NB + 1) + BB_GTRI)));
     const bool use_big = npanels > 0 && which != 4 && bt_big && n >= BB_MIN;
+    // GG_BT_SIDE=1: the three preparation launches run on a side stream next to stage 2 (fork after stage 1, join
+    // before stage 3).  The side stream belongs to the calling host thread and device (thread_local), the two events
+    // to this call: nothing is shared between concurrent solves.
+    cudaEvent_t ev_join = nullptr;
     if (use_big) {
+        cudaStream_t ps = s;
+        if (sytrd_blocked_env("GG_BT_SIDE", 0)) {
+            static thread_local cudaStream_t tl_side[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < 64) {
+                if (!tl_side[dev] && cudaStreamCreateWithFlags(&tl_side[dev], cudaStreamNonBlocking) != cudaSuccess)
+                    tl_side[dev] = nullptr;
+                cudaEvent_t ev_fork = nullptr;
+                if (tl_side[dev] && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess) {
+                    cudaEventRecord(ev_fork, s);
+                    cudaStreamWaitEvent(tl_side[dev], ev_fork, 0);
+                    ps = tl_side[dev];
+                } else ev_join = nullptr;
+                if (ev_fork) cudaEventDestroy(ev_fork);      // (released once the pending work has used it)
+            }
+        }
         const int nt64 = (n + BB_T - 1) / BB_T;
         gg_count_launch(1);
-        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, n, npb, Gb, skip);
+        bb_gram_kernel<<<dim3(BB_NB / BB_T, BB_NB / BB_T, M * npb), 256, 0, ps>>>(tw.Vh, n, npb, Gb, skip);
         gg_count_launch(1);
-        bb_x_kernel<<<dim3(npb, M), 8 * BB_NB, sizeof(double) * (BB_NB * (BB_NB + 1) + BB_GTRI), s>>>(Gb, tw.tau, n, npb, Xb, skip);
+        bb_x_kernel<<<dim3(npb, M), 8 * BB_NB, sizeof(double) * (BB_NB * (BB_NB + 1) + BB_GTRI), ps>>>(Gb, tw.tau, n, npb, Xb, skip);
         gg_count_launch(1);
-        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, s>>>(tw.Vh, Xb, n, npb, Vp, skip);
+        bb_vprime_kernel<<<dim3(nt64, BB_NB / BB_T, M * npb), 256, 0, ps>>>(tw.Vh, Xb, n, npb, Vp, skip);
         GG_CHECK_LAUNCH();
+        if (ps != s) cudaEventRecord(ev_join, ps);
     }
 
     // ---- stage 2 ----
@@ -2035,6 +2059,10 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
     // eigenvalues of the root are in lam[0]; eigenvectors of T (rows) in A
     gg_count_launch(1);
     dc_unscale_kernel<<<dim3(4, M), 256, 0, s>>>(dw.lam[0], scale, n, D, skip);
+    if (ev_join) {
+        cudaStreamWaitEvent(s, ev_join, 0);
+        cudaEventDestroy(ev_join);
+    }
     if (stop_after == 2) return 0;
 
     // ---- stage 3 ----
