@@ -447,6 +447,25 @@ def test_admm_mgl_block_eigh_path_vs_oracle(reg, K, p):
     assert abs(info["objective"][-1] - rinfo["objective"][-1]) <= 1e-6 * abs(rinfo["objective"][-1])
 
 
+@pytest.mark.parametrize("reg,K,p", [("GGL", 1, 49), ("FGL", 2, 50), ("GGL", 33, 63), ("FGL", 5, 64), ("GGL", 3, 65),
+                                      ("FGL", 90, 49), ("GGL", 2, 48)])
+def test_admm_mgl_default_loop_at_size_boundaries_vs_oracle(reg, K, p):
+    """default options (upper-triangle iteration for p > 48, full-matrix kernels at p = 48; K up to the tile limit) at
+    the sizes where the eigensolver path, the tile shapes and the K limit of the fused prox change"""
+    from gglasso_b200 import ADMM_MGL
+    from gglasso_b200.datagen import synthetic_mgl
+    from oracle import admm_oracle as orc
+    S = synthetic_mgl(K, p, N=3 * p, seed=K + p)
+    Om0 = np.repeat(np.eye(p)[None], K, 0)
+    (sol, info), _ = _quiet(ADMM_MGL, S, 0.08, 0.03, reg, Om0, tol=1e-7, rtol=1e-7)
+    ref, rinfo = orc.admm_mgl(S, 0.08, 0.03, reg, Om0, tol=1e-7, rtol=1e-7)
+    assert info["status"] == rinfo["status"]
+    for k in ("Omega", "Theta", "X"):
+        assert _rel(sol[k], ref[k]) < PER_ITER_TOL, k
+        assert np.array_equal(sol[k], sol[k].transpose(0, 2, 1)), k
+    assert np.array_equal(sol["Theta"] != 0, ref["Theta"] != 0)
+
+
 def test_input_validation_matches_reference():
     from gglasso_b200 import ADMM_MGL, ADMM_SGL
     S = np.repeat(np.eye(4)[None], 2, 0)
