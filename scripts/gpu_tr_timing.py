@@ -46,5 +46,11 @@ for lo, hi in ((1, 100), (100, 400), (400, 600), (600, js - 1)):
          "symv_waitdone_to_next_col_waitdone_us": float(np.mean(col[lo + 1:hi + 1, 1] - s[:, 1])) / 1e3,
          "per_column_us": float(np.mean(col[lo + 1:hi + 1, 1] - c[:, 1])) / 1e3}
     out[f"j{lo}-{hi}"] = d
-print(json.dumps(out, indent=1))
+per = (col[1:js, 1] - col[:js - 1, 1]) / 1e3                     # column period vs j (us)
+symv_span = (col[1:js, 1] - sv[:js - 1, 1]) / 1e3              # symv wait-done -> next column step released
+out["per_column_us_every_16"] = [[int(j), int(p - j - 1), round(float(np.median(per[j:j + 16])), 2),
+                                  round(float(np.median(symv_span[j:j + 16])), 2)] for j in range(0, js - 17, 16)]
+print(json.dumps({k: v for k, v in out.items() if k != "per_column_us_every_16"}, indent=1))
+for row in out["per_column_us_every_16"]:
+    print("j=%4d t=%4d period %6.2f us  symv->col %6.2f us" % tuple(row))
 json.dump(out, open("gpurun_out/tr_timing.json", "w"), indent=1)
