@@ -440,7 +440,10 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
 // (256, 3): 80 registers, no spills.  (256, 4) -- 64 registers, 28 bytes of spills -- was 3 % faster on a single
 // stream but produced non-finite eigenvalues for single matrices when five host threads drove five solves
 // concurrently (bisected on the B200); not understood, so not used.
-__global__ void __launch_bounds__(256, 3)
+#ifndef SV_MINB
+#define SV_MINB 3
+#endif
+__global__ void __launch_bounds__(256, SV_MINB)
 tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt,
                int r_pin)
 {
