@@ -275,6 +275,7 @@ def main():
     # ---------------- kernel-level roofline of the dominant kernel (rank 0) ----------------------------------------
     roof = kernel_roofline(st, ms / steps) if rank == 0 else None
     blocked = blocked_path_numbers(st, ms / steps) if (rank == 0 and world == 1) else None
+    prox = prox_roofline(st, cfg["reg"]) if (rank == 0 and world == 1) else None
     del st
 
     # ---------------- end to end through the public API (host buffers), `steps` iterations -------------------------
@@ -359,7 +360,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "time_to_tol": ttt_info, "parity": check,
                 "gpu_launches": launches * world, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
-                "weak": weak, "blocked_sytrd": blocked, "grid": None}
+                "weak": weak, "blocked_sytrd": blocked, "prox": prox, "grid": None}
 
     # secondary measurement, last: the headline line above is complete before it starts and is printed even if the
     # grid run fails (single process; with several ranks a failure surfaces through torchrun)
@@ -424,6 +425,53 @@ def grid_bench(world, rank, barrier, max_over_ranks):
                 "max_rel_dev_ebic": float(np.nanmax(np.abs(scores - g["bic_10x10"]) / np.abs(g["bic_10x10"]))),
                 "reference_wall_s": float(g["wall_10x10"]), "reference_cores": int(g["ref_cores"])}
     return out
+
+
+def prox_roofline(st, reg):
+    """The HBM-bound kernel class of the step (fused prox + dual update + residual sums, 5 A bytes):
+    prox_mgl_upper_kernel, timed live with CUDA events on the buffers of the finished run.  `achieved` is the
+    algorithmic 5 A over the kernel time (the kernel itself moves 2.5 A: it works on upper triangles, DESIGN.md 4.2);
+    `traffic` is the DRAM traffic of the committed ncu --set full capture of the same kernel at this size."""
+    import torch
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import _p
+    from gglasso_b200._lib import NPART
+    lib = _lib.load()
+    M, p = st.M, st.p
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        hbm, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    parts = torch.zeros((lib.gg_mgl_upper_nparts(p), NPART), dtype=torch.float64, device=st.dev)
+    from gglasso_b200._lib import C_DONE
+    ctrl = st.ctrl.clone()
+    ctrl[:, C_DONE] = 0.0                              # (the kernel is a no-op for a finished problem)
+    stream = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for r in range(12):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = lib.gg_prox_mgl_upper(_p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta), _p(ctrl), CFG["lambda1"],
+                                   CFG["lambda2"], 0 if reg == "GGL" else 1, M, p, _p(parts), stream)
+        b.record()
+        torch.cuda.synchronize()
+        assert rc == 0, rc
+        if r >= 2:
+            ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    alg = 5.0 * 8.0 * M * p * p
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))["prox_mgl_upper_kernel"]
+        if tr["K"] == M and tr["p"] == p:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": f"prox_mgl_upper_kernel<{reg}>", "achieved": alg / ms / 1e6, "peak": hbm,
+            "unit": "GB/s", "frac": alg / ms / 1e6 / hbm, "traffic": traffic, "ms": ms, "algorithmic_bytes": alg,
+            "moved_bytes": alg / 2, "frac_of_moved_bytes": alg / 2 / ms / 1e6 / hbm, "peak_source": peak_src,
+            "note": "works on upper triangles only: 2.5 A moved for the 5 A step it replaces"}
 
 
 def kernel_roofline(st, ms_per_step):
