@@ -40,6 +40,8 @@ SIGNATURES = {
     "gg_prox_mgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_add3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "gg_pack_bands": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "gg_pack_bands_p2p": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "gg_prox_band_p2p": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, _i, _i, _i, _i, _vp]),
     "gg_unpack_dual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gg_prox_band": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, _i, _i, _i, _vp]),
     "gg_ext_theta": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

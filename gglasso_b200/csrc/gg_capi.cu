@@ -38,6 +38,10 @@ int gg_launch_ext_dual(double*, double*, const double*, const double*, const dou
                        const double*, const double*, const int*, int, int, double*, cudaStream_t);
 int gg_launch_prox_band(const double*, double*, const double*, double, double, int, int, int, int, int, cudaStream_t);
 int gg_launch_pack_bands(const double*, const double*, const double*, const double*, int, int, int, double*, cudaStream_t);
+int gg_launch_pack_bands_p2p(const double*, const double*, const double*, const double*, int, int, int, int, double* const*,
+                             cudaStream_t);
+int gg_launch_prox_band_p2p(const double*, double* const*, const double*, double, double, int, int, int, int, int, int,
+                            cudaStream_t);
 int gg_launch_unpack_dual(const double*, const double*, const double*, double*, double*, double*, const double*, int, int,
                           int, double*, cudaStream_t);
 size_t gg_tridiag_ws_bytes(int, int);
@@ -192,6 +196,21 @@ int gg_pack_bands(const double* Omega, const double* L, const double* X, const d
 {
     if (K_loc <= 0 || p <= 0 || world <= 0 || world > p) return -1;
     return gg_launch_pack_bands(Omega, L, X, ctrl, K_loc, p, world, send, (cudaStream_t)stream);
+}
+
+int gg_pack_bands_p2p(const double* Omega, const double* L, const double* X, const double* ctrl, int K_loc, int p,
+                      int world, int k_lo, double* const* peer_band, void* stream)
+{
+    if (K_loc <= 0 || p <= 0 || world <= 0 || world > 16 || world > p || k_lo < 0 || peer_band == nullptr) return -1;
+    return gg_launch_pack_bands_p2p(Omega, L, X, ctrl, K_loc, p, world, k_lo, peer_band, (cudaStream_t)stream);
+}
+
+int gg_prox_band_p2p(const double* V, double* const* peer_back, const double* ctrl, double lambda1, double lambda2,
+                     int reg, int K, int nb, int p, int row0, int world, void* stream)
+{
+    if (K <= 0 || nb < 0 || p <= 0 || reg < 0 || reg > 1 || world <= 0 || world > 16 || peer_back == nullptr) return -1;
+    return gg_launch_prox_band_p2p(V, peer_back, ctrl, lambda1, lambda2, reg, K, nb, p, row0, world,
+                                   (cudaStream_t)stream);
 }
 
 int gg_unpack_dual(const double* recv, const double* Omega, const double* Omega_prev, double* X, double* Theta,

@@ -732,6 +732,86 @@ prox_band_kernel(const double* __restrict__ V, double* __restrict__ Theta, const
 }
 
 // ------------------------------------------------------------------------------------------
+// Peer-memory variants of the two exchange steps of the K-sharded loop (one process per GPU, buffers in symmetric
+// memory, peer pointers mapped over NVLink): the kernels store straight into the receive buffers of the other ranks,
+// so the re-tile IS the exchange -- no send buffer, no all-to-all; the host only puts a cross-rank barrier after each.
+#define GG_MAX_PEERS 16
+struct GgPeers { double* ptr[GG_MAX_PEERS]; };
+
+__device__ __forceinline__ void gg_part(int n, int world, int idx, int& lo, int& len)
+{   // parallel.partition(): the first n % world parts are one longer
+    const int base = n / world, rem = n - base * world;
+    lo = idx < rem ? idx * (base + 1) : rem * (base + 1) + (idx - rem) * base;
+    len = base + (idx < rem ? 1 : 0);
+}
+
+// band buffer of rank d: (K_total, rows_d, p).  This rank's instances are k_lo .. k_lo + K_loc - 1.
+__global__ void __launch_bounds__(EW_THREADS)
+pack_bands_p2p_kernel(const double* __restrict__ Omega, const double* __restrict__ L, const double* __restrict__ X,
+                      const double* __restrict__ ctrl, int p, int K_loc, int world, int k_lo, GgPeers band)
+{
+    if (ctrl && ctrl[GG_C_DONE] != 0.0) return;
+    const int m = blockIdx.y;
+    const size_t pp = (size_t)p * p, base = (size_t)m * pp;
+    const int rb = p / world, rem = p - rb * world, cut = rem * (rb + 1);
+    for (size_t e = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; e < pp; e += (size_t)gridDim.x * EW_THREADS) {
+        const int r = (int)(e / p), c = (int)(e - (size_t)r * p);
+        const int d = r < cut ? r / (rb + 1) : rem + (r - cut) / rb;
+        const int lo = d < rem ? d * (rb + 1) : cut + (d - rem) * rb;
+        const int rows = rb + (d < rem ? 1 : 0);
+        double v = Omega[base + e];
+        if (L) v = v + L[base + e];
+        band.ptr[d][((size_t)(k_lo + m) * rows + (r - lo)) * p + c] = v + X[base + e];
+    }
+}
+
+// prox on the local band (K, nb, p) of all instances; Theta of instance k goes to its owner's `back` buffer, which is
+// laid out like the send / receive buffers of the all-to-all version: [band d][m][row][col], band d at offset
+// K_loc(owner) * p * row0_d.
+template <int REG>
+__global__ void __launch_bounds__(256)
+prox_band_p2p_kernel(const double* __restrict__ V, GgPeers back, const double* __restrict__ ctrl, double lambda1,
+                     double lambda2, int K, int nb, int p, int row0, int world)
+{
+    extern __shared__ double ysm[];              // K * blockDim.x doubles
+    if (ctrl[GG_C_DONE] != 0.0) return;
+    const double inv_rho = 1.0 / ctrl[GG_C_RHO];
+    if (ctrl[GG_C_LAM1] > 0.0) { lambda1 = ctrl[GG_C_LAM1]; lambda2 = ctrl[GG_C_LAM2]; }
+    const double l1 = inv_rho * lambda1, l2 = inv_rho * lambda2;
+    const int T = blockDim.x;
+    const size_t slab = (size_t)nb * p;
+    const size_t e = (size_t)blockIdx.x * T + threadIdx.x;
+    if (e >= slab) return;
+    const int r = (int)(e / p), c = (int)(e - (size_t)r * p);
+    double* y = ysm + threadIdx.x;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) y[k * T] = V[k * slab + e];
+    if (row0 + r != c) {
+        if (REG == 0) {
+            double ss = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double u = gg_soft(y[k * T], l1);
+                y[k * T] = u;
+                ss += u * u;
+            }
+            const double nrm = sqrt(ss);
+            const double a = nrm > l2 ? nrm : l2;
+            const double f = a - l2;
+            for (int k = 0; k < K; ++k) y[k * T] = (y[k * T] * f) / a;
+        } else {
+            gg_tv1d_inplace(y, K, T, l2);
+            for (int k = 0; k < K; ++k) y[k * T] = gg_soft(y[k * T], l1);
+        }
+    }
+    for (int s = 0; s < world; ++s) {
+        int k0, kl;
+        gg_part(K, world, s, k0, kl);
+        double* dst = back.ptr[s] + (size_t)kl * p * row0 + e;
+        for (int m = 0; m < kl; ++m) dst[(size_t)m * slab] = y[(k0 + m) * T];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // ext_ADMM_MGL (non-conforming group graphical lasso, src/gglasso/solver/ext_admm_solver.py:191-273).
 // The K matrices of different size p_k are padded to a common p (decoupled unit diagonal, see block_SGL);
 // pvec[k] = p_k masks the padding out of the norms.  One ADMM problem, rho fixed.
@@ -1075,6 +1155,43 @@ int gg_launch_prox_band(const double* V, double* Theta, const double* ctrl, doub
         if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         gg_count_launch(1);
         prox_band_kernel<1><<<grid, T, smem, st>>>(V, Theta, ctrl, l1, l2, K, nb, p, row0);
+    }
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_pack_bands_p2p(const double* Omega, const double* L, const double* X, const double* ctrl, int K_loc,
+                             int p, int world, int k_lo, double* const* peer_band, cudaStream_t st)
+{
+    GgPeers pb;
+    for (int i = 0; i < GG_MAX_PEERS; ++i) pb.ptr[i] = i < world ? peer_band[i] : nullptr;
+    dim3 grid(gg_sgl_nparts(p, K_loc), K_loc);
+    gg_count_launch(1);
+    pack_bands_p2p_kernel<<<grid, EW_THREADS, 0, st>>>(Omega, L, X, ctrl, p, K_loc, world, k_lo, pb);
+    GG_CHECK_LAUNCH();
+    return 0;
+}
+
+int gg_launch_prox_band_p2p(const double* V, double* const* peer_back, const double* ctrl, double l1, double l2, int reg,
+                            int K, int nb, int p, int row0, int world, cudaStream_t st)
+{
+    GgPeers pb;
+    for (int i = 0; i < GG_MAX_PEERS; ++i) pb.ptr[i] = i < world ? peer_back[i] : nullptr;
+    int T = 256;
+    while (T > 32 && (size_t)K * T * sizeof(double) > 96 * 1024) T >>= 1;
+    const size_t smem = (size_t)K * T * sizeof(double);
+    if (smem > 200 * 1024) return -2;
+    const size_t slab = (size_t)nb * p;
+    const unsigned grid = (unsigned)((slab + T - 1) / T);
+    if (grid == 0) return 0;
+    if (reg == 0) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_p2p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gg_count_launch(1);
+        prox_band_p2p_kernel<0><<<grid, T, smem, st>>>(V, pb, ctrl, l1, l2, K, nb, p, row0, world);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(prox_band_p2p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gg_count_launch(1);
+        prox_band_p2p_kernel<1><<<grid, T, smem, st>>>(V, pb, ctrl, l1, l2, K, nb, p, row0, world);
     }
     GG_CHECK_LAUNCH();
     return 0;

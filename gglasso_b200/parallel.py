@@ -17,6 +17,8 @@ Three natural seams:
 
 The re-tile helpers work on CPU tensors over gloo as well, which is how the host logic is tested without GPUs.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -118,6 +120,69 @@ def ADMM_MGL_dist(S_local, lambda1, lambda2, reg, Omega_0_local, **kw):
     return sol, info
 
 
+LAST_EXCHANGE = None        # how the last K-sharded solve exchanged its bands (diagnostics / tests)
+
+
+class _P2PExchange:
+    """receive buffers of the K-sharded loop in symmetric memory (torch.distributed._symmetric_memory): every rank
+    allocates the same sizes (maxima over ranks), maps the peers' buffers and hands their device pointers to
+    gg_pack_bands_p2p / gg_prox_band_p2p; `barrier` is the symmetric-memory barrier on the current stream."""
+
+    def __init__(self, sh, dev):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        group = sh.group if sh.group is not None else dist.group.WORLD
+        p, world = sh.p, sh.world
+        nb_max = max(hi - lo for lo, hi in sh.rparts)
+        kl_max = max(hi - lo for lo, hi in sh.kparts)
+        self.band_full = symm.empty(sh.K_total * nb_max * p, dtype=torch.float64, device=dev)
+        self.back_full = symm.empty(kl_max * p * p, dtype=torch.float64, device=dev)
+        self.hb = symm.rendezvous(self.band_full, group)
+        self.hk = symm.rendezvous(self.back_full, group)
+        self.band = self.band_full[:sh.K_total * sh.nb * p]
+        self.back = self.back_full[:sh.K_loc * p * p]
+        self.back.zero_()
+        arr = ctypes.c_void_p * 16
+        self.band_ptrs = arr(*[int(x) for x in self.hb.buffer_ptrs])
+        self.back_ptrs = arr(*[int(x) for x in self.hk.buffer_ptrs])
+        self.timeout_ms = int(os.environ.get("GG_DIST_P2P_TIMEOUT_MS", "20000"))
+
+    def barrier(self, channel):
+        self.hb.barrier(channel=channel, timeout_ms=self.timeout_ms)
+
+
+_P2P_CACHE = {}
+
+
+def _p2p_exchange(sh, dev):
+    """None (with one warning) when symmetric memory cannot be set up on this machine: the NCCL all-to-all path runs.
+    The buffers and the rendezvous are kept per (group, K_total, p): setting them up costs ~100 ms."""
+    key = (id(sh.group), sh.K_total, sh.p, sh.world, dev.index)
+    if key in _P2P_CACHE:
+        return _P2P_CACHE[key]
+    _P2P_CACHE[key] = ex = _p2p_exchange_new(sh, dev)
+    return ex
+
+
+def _p2p_exchange_new(sh, dev):
+    try:
+        ok = torch.tensor([1], dtype=torch.int32, device=dev)
+        try:
+            ex = _P2PExchange(sh, dev)
+        except Exception as e:                          # noqa: BLE001  (any failure -> every rank must fall back)
+            ex, ok[0] = None, 0
+            import warnings
+            warnings.warn(f"gglasso_b200: peer-memory exchange unavailable ({type(e).__name__}: {str(e)[:160]}); "
+                          "using NCCL all-to-all")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=sh.group)
+        if int(ok.item()) != 1:
+            return None
+        ex.barrier(2)                                   # every rank's buffers exist and are zeroed
+        return ex
+    except Exception:                                    # noqa: BLE001
+        return None
+
+
 def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=None, Theta_0_local=None,
                       X_0_local=None, n_samples=None, tol=1e-5, rtol=1e-4, update_rho=True, rho=1., max_iter=1000,
                       verbose=False, latent=False, mu1_local=None, group=None, check_every=1):
@@ -151,23 +216,40 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
     # kernels are no-ops and Theta stays what the last executed iteration produced), `back` = Theta of the local
     # instances, band by band.  With one rank the exchanges are the identity and the buffers alias.
     loc_n, band_n = K_loc * p * p, K_total * sh.nb * p
-    send = torch.empty(loc_n, dtype=torch.float64, device=st.dev)
-    band = torch.empty(band_n, dtype=torch.float64, device=st.dev) if sh.world > 1 else send
-    tband = torch.zeros(band_n, dtype=torch.float64, device=st.dev)
-    back = torch.empty(loc_n, dtype=torch.float64, device=st.dev) if sh.world > 1 else tband
+    p2p = _p2p_exchange(sh, st.dev) if (sh.world > 1 and os.environ.get("GG_DIST_P2P", "0") == "1") else None
+    global LAST_EXCHANGE
+    LAST_EXCHANGE = "single rank" if sh.world == 1 else ("peer memory" if p2p is not None else "nccl all-to-all")
+    if p2p is None:
+        send = torch.empty(loc_n, dtype=torch.float64, device=st.dev)
+        band = torch.empty(band_n, dtype=torch.float64, device=st.dev) if sh.world > 1 else send
+        tband = torch.zeros(band_n, dtype=torch.float64, device=st.dev)
+        back = torch.empty(loc_n, dtype=torch.float64, device=st.dev) if sh.world > 1 else tband
+    else:
+        band, back = p2p.band, p2p.back
     loc_split = [K_loc * (hi - lo) * p for lo, hi in sh.rparts]
     band_split = [(khi - klo) * sh.nb * p for klo, khi in sh.kparts]
 
     for it in range(max_iter):
         st.omega_step()
-        _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), K_loc, p, sh.world, _p(send),
-                                     stream), "gg_pack_bands")
-        if sh.world > 1:
-            dist.all_to_all_single(band, send, band_split, loc_split, group=sh.group)
-        _lib.check(lib.gg_prox_band(_p(band), _p(tband), _p(st.ctrl), float(lambda1), float(lambda2), regi, K_total,
-                                    sh.nb, p, sh.r_lo, stream), "gg_prox_band")
-        if sh.world > 1:
-            dist.all_to_all_single(back, tband, loc_split, band_split, group=sh.group)
+        if p2p is not None:
+            # the re-tile kernels store straight into the peers' buffers over NVLink; a barrier after each replaces
+            # the all-to-all.  Buffers are reused safely: a rank passes the second barrier only
+            # when every rank has finished its prox (= has read its band), and the first one only after its own unpack.
+            _lib.check(lib.gg_pack_bands_p2p(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), K_loc, p, sh.world,
+                                             sh.k_lo, p2p.band_ptrs, stream), "gg_pack_bands_p2p")
+            p2p.barrier(0)
+            _lib.check(lib.gg_prox_band_p2p(_p(band), p2p.back_ptrs, _p(st.ctrl), float(lambda1), float(lambda2), regi,
+                                            K_total, sh.nb, p, sh.r_lo, sh.world, stream), "gg_prox_band_p2p")
+            p2p.barrier(1)
+        else:
+            _lib.check(lib.gg_pack_bands(_p(st.Omega_new), _p(st.L), _p(st.X), _p(st.ctrl), K_loc, p, sh.world,
+                                         _p(send), stream), "gg_pack_bands")
+            if sh.world > 1:
+                dist.all_to_all_single(band, send, band_split, loc_split, group=sh.group)
+            _lib.check(lib.gg_prox_band(_p(band), _p(tband), _p(st.ctrl), float(lambda1), float(lambda2), regi, K_total,
+                                        sh.nb, p, sh.r_lo, stream), "gg_prox_band")
+            if sh.world > 1:
+                dist.all_to_all_single(back, tband, loc_split, band_split, group=sh.group)
         # Theta back in instance layout, fused with the dual update and the residual sums (non-latent) or with
         # C = Theta - X - Omega for the L step (latent)
         _lib.check(lib.gg_unpack_dual(_p(back), _p(st.Omega_new), _p(st.Omega), _p(st.X), _p(st.Theta),

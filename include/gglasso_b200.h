@@ -140,6 +140,16 @@ int gg_pack_bands(const double* Omega, const double* L, const double* X, const d
                   double* send, void* stream);
 int gg_unpack_dual(const double* recv, const double* Omega, const double* Omega_prev, double* X, double* Theta,
                    double* C, const double* ctrl, int K_loc, int p, int world, double* partials, void* stream);
+
+/* Peer-memory variants of the two exchange steps (buffers in symmetric memory, peer_*[r] = device pointer of rank
+ * r's buffer as mapped into this process, world <= 16): gg_pack_bands_p2p stores V = (Omega+L)+X of this rank's
+ * instances (global indices k_lo ..) straight into every rank's band buffer (K_total, rows_d, p); gg_prox_band_p2p
+ * runs the band prox and stores Theta of instance k into its owner's receive buffer (layout of gg_unpack_dual's
+ * `recv`).  The caller places a cross-rank barrier after each.  Same arithmetic as gg_pack_bands / gg_prox_band. */
+int gg_pack_bands_p2p(const double* Omega, const double* L, const double* X, const double* ctrl, int K_loc, int p,
+                      int world, int k_lo, double* const* peer_band, void* stream);
+int gg_prox_band_p2p(const double* V, double* const* peer_back, const double* ctrl, double lambda1, double lambda2,
+                     int reg, int K, int nb, int p, int row0, int world, void* stream);
 int gg_prox_band(const double* V, double* Theta, const double* ctrl, double lambda1, double lambda2, int reg,
                  int K, int nb, int p, int row0, void* stream);
 

@@ -31,6 +31,8 @@ def main():
                                                        status=info["status"], ref_status=rinfo["status"],
                                                        pattern_equal=bool(np.array_equal(sol["Theta"] != 0, ref["Theta"][lo:hi] != 0)))
     if rank == 0:
+        from gglasso_b200 import parallel
+        print("DIST_EXCHANGE", parallel.LAST_EXCHANGE)
         print("DIST_CHECK", json.dumps(out))
         ok = all(v["maxerr"] < 1e-9 and v["iters"] == v["ref_iters"] and v["status"] == v["ref_status"] and v["pattern_equal"] for v in out.values())
         print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAIL")

@@ -578,18 +578,22 @@ def test_admm_mgl_large_K_all_options(kw):
         assert out.startswith("------------ADMM Algorithm for Multiple Graphical Lasso----------------")
 
 
-def test_k_sharded_two_ranks_nccl():
-    """2-GPU check (skipped on a 1-GPU box): K-sharded solve with the all-to-all re-tile vs the single-GPU solve."""
+@pytest.mark.parametrize("exchange", ["nccl all-to-all", "peer memory"])
+def test_k_sharded_two_ranks_nccl(exchange):
+    """2-GPU check (skipped on a 1-GPU box): K-sharded solve vs the single-GPU solve, with the NCCL all-to-all re-tile
+    and with the kernels that store straight into the peers' buffers (GG_DIST_P2P=1, symmetric memory)."""
     import os
     import subprocess
     import sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GG_DIST_P2P="1" if exchange == "peer memory" else "0")
     o = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_check.py")],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=env)
     assert "DIST_CHECK_OK" in o.stdout, o.stdout[-2000:] + o.stderr[-2000:]
+    assert f"DIST_EXCHANGE {exchange}" in o.stdout, o.stdout[-2000:]
 
 
 def test_block_sgl_ragged_batches_vs_oracle():
