@@ -355,6 +355,9 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, **CFG,
                            "l2": "inputs larger than L2 (each (K,p,p) FP64 array is 160 MB; >10 arrays per step)",
+                           "host_polling": "value: the timed region enqueues all steps without reading the device "
+                                           "(tol = 0); e2e and time_to_tol: public call, control block read every "
+                                           "iteration as in normal use",
                            "K_total": K, "partition": shard, "input_fingerprint_dev": in_dev,
                            "eigh": "sytrd (per-column chain, lazy write-back) + divide&conquer + blocked ormtr, hand-written"},
                 "e2e": {"value": e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
