@@ -91,6 +91,11 @@ __device__ __forceinline__ double tr_block_allsum(double v, double* scratch)
 // (The body is shared by tr_col_kernel and by tr_step_kernel, where the CTA that finishes the last tile of a matrix
 //  runs it for the next column: row j and y are then data written by other CTAs of the SAME grid, hence the
 //  ld.global.cg loads -- L2 is the point of coherence, the fences are in tr_step_kernel.)
+#ifdef TR_COL_PLAIN
+#define TR_CLD(p) (*(p))
+#else
+#define TR_CLD(p) __ldcg(p)
+#endif
 template <int EPT, bool PREF>
 __device__ __forceinline__ void tr_col_body(const double* A, int n, int j, int kb, const TrWs& ws, int m, int sk,
                                             bool stamp_on)
@@ -115,12 +120,12 @@ __device__ __forceinline__ void tr_col_body(const double* A, int n, int j, int k
     for (int e = 0; e < EPT; ++e) {
         const int i = j + tid + e * nt;
         const bool ok = i < n;
-        a[e] = ok ? __ldcg(rowj + i) : 0.0;
-        yv[e] = (ok && j >= 1) ? __ldcg(y + i) : 0.0;
+        a[e] = ok ? TR_CLD(rowj + i) : 0.0;
+        yv[e] = (ok && j >= 1) ? TR_CLD(y + i) : 0.0;
         vp[e] = (ok && j >= 1) ? vprev[i] : 0.0;
     }
     double tp = 0.0, yj = 0.0;
-    if (j >= 1) { tp = tau[j - 1]; yj = __ldcg(y + j); }
+    if (j >= 1) { tp = tau[j - 1]; yj = TR_CLD(y + j); }
     // older pending pairs kb..j-2 (independent of w_{j-1}): a_i -= v_k[i] w_k[j] + w_k[i] v_k[j]
     // (PREF: fully unrolled with predicates so that all of these loads are in flight together with the ones above;
     //  the large-p variant keeps them in a loop -- no register spills in any kernel of the launch chain)
@@ -256,27 +261,13 @@ struct SvSmem {
     double colp[16][SV_T];                       // [ty][col] partial column sums
 };
 
-// L2 residency control of the trailing-matrix sweep.  The 2p passes of a tridiagonalisation re-read the same (shrinking)
-// set of upper triangles; while that set is larger than the L2 an LRU-like policy evicts every line before its reuse and
-// each pass comes from HBM.  The bottom-right part of every matrix (rows >= r_pin) belongs to ALL later passes: its
-// tiles are loaded / stored with an evict_last policy, the rest with evict_first, so that a fixed ~64 MB of the batch
-// stays resident from the second pass on.  hint == 0: plain ld.global.cg / st (batches that fit the L2 anyway).
-__device__ __forceinline__ double sv_ld(const double* p, int hint, unsigned long long pol)
-{
-    if (!hint) return __ldcg(p);
-    double v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void sv_st(double* p, double v, int hint, unsigned long long pol)
-{
-    if (!hint) { *p = v; return; }
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
-}
-
+// (Round 2 tried L2 cache-policy hints on these loads / stores -- evict_last for a pinned bottom-right part of every
+//  matrix, evict_first for the rest: no gain for the chain, and the extra predicates in the unrolled load / store
+//  loops cost 0.34 ms per tridiagonalisation at K=20, p=1000 even when switched off; removed.  The blocked path's
+//  panel kernel keeps its own hints, where they are worth 3.5 ms.)
 template <bool INTERIOR>
 __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int j, int kb, int write, const TrWs& ws,
-                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm, int r_pin,
+                                             const int* __restrict__ skip, int m, int I, int J, SvSmem& sm,
                                              int pdl, bool& skipped)
 {
     skipped = true;
@@ -301,17 +292,11 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
     }
     double a[4][4];
     unsigned okm = 0xffffu;
-    const int hint = r_pin >= 0;
-    unsigned long long pol = 0;
-    if (hint) {
-        if (base + r0 >= r_pin) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-        else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    }
     if (INTERIOR) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) a[i][jj] = sv_ld(pt + (size_t)i * n + 16 * jj, hint, pol);
+            for (int jj = 0; jj < 4; ++jj) a[i][jj] = __ldcg(pt + (size_t)i * n + 16 * jj);
     } else {
         okm = 0;
 #pragma unroll
@@ -321,7 +306,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
                 const int r = rb + i, c = cb + 16 * jj;
                 const bool ok = (r < t && c < t && c >= r);
                 okm |= ok ? (1u << (4 * i + jj)) : 0u;
-                a[i][jj] = ok ? sv_ld(pt + (size_t)i * n + 16 * jj, hint, pol) : 0.0;
+                a[i][jj] = ok ? __ldcg(pt + (size_t)i * n + 16 * jj) : 0.0;
             }
     }
     if (pdl != 2) asm volatile("griddepcontrol.wait;" ::: "memory");   // everything below reads what the column step wrote
@@ -388,7 +373,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-                if (INTERIOR || (okm & (1u << (4 * i + jj)))) sv_st(pt + (size_t)i * n + 16 * jj, a[i][jj], hint, pol);
+                if (INTERIOR || (okm & (1u << (4 * i + jj)))) pt[(size_t)i * n + 16 * jj] = a[i][jj];
     }
 #ifdef TR_TIMING
     if (a[0][0] == 1.2345e300) return;       // (forces the tile loads to have landed before the stamp)
@@ -444,8 +429,7 @@ __device__ __forceinline__ void sv_tile_body(double* __restrict__ A, int n, int 
 #define SV_MINB 3
 #endif
 __global__ void __launch_bounds__(256, SV_MINB)
-tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt,
-               int r_pin)
+tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt)
 {
     __shared__ SvSmem sm;
     // Boustrophedon sweep: consecutive launches walk the (matrix, tile) space in opposite directions, so a launch
@@ -463,8 +447,8 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
     asm volatile("griddepcontrol.launch_dependents;");       // let the next grid in the chain become resident
     const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
     bool skipped;
-    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, 0, skipped);
-    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, 0, skipped);
+    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, 0, skipped);
+    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, 0, skipped);
 }
 
 // tr_symv_kernel(j) followed, in the same launch, by the column step j+1 (tr_col_body): the CTA that finishes the last
@@ -473,7 +457,7 @@ tr_symv_kernel(double* __restrict__ A, int n, int j, int kb, int write, TrWs ws,
 // Ordering: every thread fences its atomics on y / stores of A before the CTA's arrival; the last CTA fences again
 // before it reads y and row j+1 (ld.global.cg).  col_next = 0 on the last chain step (tr_tail_kernel continues).
 __global__ void __launch_bounds__(256, 3)
-tr_step_kernel(double* A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt, int r_pin,
+tr_step_kernel(double* A, int n, int j, int kb, int write, TrWs ws, const int* __restrict__ skip, int nt,
                int early, int col_next)
 {
     __shared__ SvSmem sm;
@@ -489,8 +473,8 @@ tr_step_kernel(double* A, int n, int j, int kb, int write, TrWs ws, const int* _
     TR_STAMP(1, 0);
     const bool interior = (I < J) && ((J + 1) * SV_T <= n - j - 1);
     bool skipped;
-    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, early ? 1 : 2, skipped);
-    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, r_pin, early ? 1 : 2, skipped);
+    if (interior) sv_tile_body<true>(A, n, j, kb, write, ws, skip, m, I, J, sm, early ? 1 : 2, skipped);
+    else sv_tile_body<false>(A, n, j, kb, write, ws, skip, m, I, J, sm, early ? 1 : 2, skipped);
     if (skipped || !col_next) return;         // (block-uniform)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1874,15 +1858,6 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
             }
         }
         const bool chain = !(use_blocked && prof12) && jb < js;
-        // rows >= r_pin of every matrix are kept in L2 (evict_last) by the chain's trailing-matrix passes: the largest
-        // bottom-right triangle with 4 M (n - r_pin)^2 <= GG_TR_CHAIN_L2MB megabytes; -1: no hints
-        int r_pin = -1;
-        {
-            // (no measurable effect on the chain at K=20, p=1000 -- 12.05 vs 11.97 ms -- so it is off unless asked for;
-            //  the blocked path's streamed strips gain 3.5 ms from the same hints and use them by default)
-            const double l2b = (double)sytrd_blocked_env("GG_TR_CHAIN_L2MB", 0) * 1048576.0;
-            if (l2b > 0.0 && 4.0 * M * (double)n * n > l2b) r_pin = n - (int)floor(sqrt(l2b / (4.0 * M)));
-        }
         const int lazy_q = gg_tr_lazy_depth();
         int kb = jb;                                  // pairs kb..j-1 are pending at step j
         // merged chain (GG_TR_MERGE=1, n - jb <= 2048): column step jb alone, then one tr_step_kernel per column.
@@ -1913,7 +1888,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 gg_count_launch(1);
                 // the grid after the standalone column kernel must not load early either: that kernel releases its
                 // dependents after ITS wait, but the grid before it may be a blocked-path kernel without the protocol
-                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_step_kernel, A, n, j, kb, write, tw, (const int*)skip, nt, r_pin,
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_step_kernel, A, n, j, kb, write, tw, (const int*)skip, nt,
                                                    (prev_write || j == jb) ? 0 : 1, (j + 1 < js) ? 1 : 0);
                 if (e != cudaSuccess) return (int)e;
                 prev_write = write;
@@ -1941,7 +1916,7 @@ int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl,
                 const int nt = (t + SV_T - 1) / SV_T;
                 cfg.gridDim = dim3(nt * (nt + 1) / 2, M); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
                 gg_count_launch(1);
-                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, kb, write, tw, (const int*)skip, nt, r_pin);
+                cudaError_t e = cudaLaunchKernelEx(&cfg, tr_symv_kernel, A, n, j, kb, write, tw, (const int*)skip, nt);
                 if (e != cudaSuccess) return (int)e;
             }
             if (write) kb = j;
