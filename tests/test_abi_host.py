@@ -118,3 +118,27 @@ def test_write_depth_and_launch_counter(lib):
     # gg_launch_count is a monotonic process-wide counter of this library's kernel launches; without a GPU nothing
     # is launched, so it only has to be readable here (bench.py takes differences around its timed region)
     assert lib.gg_launch_count() >= 0
+
+
+def test_upper_triangle_tile_grid_covers_every_upper_entry_once(lib):
+    """host statement of prox_mgl_upper_kernel's block -> tile map (gg_elementwise.cu: tiles of 8 rows x 32 columns,
+    tile rows grouped by four, group g starting at tile column g): gg_mgl_upper_nparts(p) tiles, and every entry
+    i <= j < p lies in exactly one of them"""
+    UT_R, UT_C = 8, 32
+    for p in (1, 7, 8, 31, 32, 33, 49, 100, 257, 1000):
+        n = lib.gg_mgl_upper_nparts(p)
+        nc, gr = (p + UT_C - 1) // UT_C, UT_C // UT_R
+        nr = (p + UT_R - 1) // UT_R
+        assert n == sum(nc - (I * UT_R) // UT_C for I in range(nr))
+        cover = np.zeros((p, p), dtype=np.int32)
+        for b in range(n):
+            rem, g = b, 0
+            while rem >= gr * (nc - g):
+                rem -= gr * (nc - g)
+                g += 1
+            I, J = g * gr + rem // (nc - g), g + rem % (nc - g)
+            r0, c0 = I * UT_R, J * UT_C
+            assert r0 < p, (p, b)
+            cover[r0:r0 + UT_R, c0:c0 + UT_C] += 1
+        iu = np.triu_indices(p)
+        assert np.all(cover[iu] == 1), p
