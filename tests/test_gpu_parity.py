@@ -536,6 +536,51 @@ def test_pack_unpack_band_kernels(K_loc, p, world):
             np.testing.assert_allclose(parts.sum(0).cpu().numpy(), want, rtol=1e-12)
 
 
+@pytest.mark.parametrize("reg,K,p,world", [("GGL", 7, 45, 4), ("FGL", 20, 33, 8), ("FGL", 5, 64, 2), ("GGL", 3, 10, 3)])
+def test_peer_memory_exchange_kernels_on_one_device(reg, K, p, world):
+    """gg_pack_bands_p2p / gg_prox_band_p2p with every "rank" played in turn on one GPU (the peer pointers are local
+    buffers): uneven instance and row partitions, result = prox_p of the whole stack in gg_unpack_dual's layout"""
+    import ctypes
+    from gglasso_b200 import _lib
+    from gglasso_b200._engine import to_dev, _p
+    from gglasso_b200.parallel import partition, band_layout_index
+    from oracle import admm_oracle as orc
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(K * 10 + p + world)
+    Om = np.stack([_sym(rng, p, 0.3) for _ in range(K)])
+    X = np.stack([_sym(rng, p, 0.2) for _ in range(K)])
+    rho, l1, l2 = 2.0, 0.21, 0.13
+    want = orc.prox_p(Om + X, l1 / rho, l2 / rho, reg)
+    kparts, rparts = partition(K, world), partition(p, world)
+    bands = [torch.full((K * (hi - lo) * p,), np.nan, dtype=torch.float64, device=dev) for lo, hi in rparts]
+    backs = [torch.full((max(1, (hi - lo)) * p * p,), np.nan, dtype=torch.float64, device=dev) for lo, hi in kparts]
+    arr = ctypes.c_void_p * 16
+    band_ptrs = arr(*[b.data_ptr() for b in bands])
+    back_ptrs = arr(*[b.data_ptr() for b in backs])
+    ctrl = _ctrl(dev, rho)
+    for (klo, khi) in kparts:                                   # every rank packs its instances into all band buffers
+        if khi == klo:
+            continue
+        dO, dX = to_dev(Om[klo:khi], dev), to_dev(X[klo:khi], dev)
+        assert lib.gg_pack_bands_p2p(_p(dO), None, _p(dX), _p(ctrl), khi - klo, p, world, klo, band_ptrs, 0) == 0
+    torch.cuda.synchronize()
+    for d, (lo, hi) in enumerate(rparts):                        # band buffer of rank d = rows lo..hi of V, all instances
+        got = bands[d].cpu().numpy().reshape(K, hi - lo, p)
+        assert np.array_equal(got, (Om + X)[:, lo:hi, :])
+        if hi > lo:
+            assert lib.gg_prox_band_p2p(_p(bands[d]), back_ptrs, _p(ctrl), l1, l2, 0 if reg == "GGL" else 1, K, hi - lo,
+                                        p, lo, world, 0) == 0
+    torch.cuda.synchronize()
+    for s, (klo, khi) in enumerate(kparts):                      # receive buffer of rank s, in gg_unpack_dual's layout
+        if khi == klo:
+            continue
+        idx = band_layout_index(khi - klo, p, world)
+        got = backs[s].cpu().numpy()[idx]
+        assert np.abs(got - want[klo:khi]).max() < 1e-15
+        assert np.array_equal(got != 0, want[klo:khi] != 0)
+
+
 @pytest.mark.parametrize("reg,latent", [("FGL", False), ("GGL", True)])
 def test_k_sharded_check_every_keeps_converged_state(reg, latent):
     """iterations enqueued after convergence (check_every > 1) are no-ops: Theta / X / Omega are those of the last
