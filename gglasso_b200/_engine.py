@@ -468,7 +468,7 @@ def run_admm(kind, S, Omega_0, Theta_0, X_0, *, lambda1, lambda2=None, reg=None,
     # current (every consumer inside the loop reads nothing else; half the elementwise HBM traffic) and the lower
     # triangles are filled once after the loop -- prox_p's mirroring (ggl_helper.py:198-205) done once.
     upper = (kind == "mgl" and not latent and not big_K and stopping_criterion == "boyd" and not measure
-             and not _DEBUG_KEEP_INPUT and st.eig.nb2 == 0 and p > _env_int("GG_JACOBI_MAX", 48)
+             and not _DEBUG_KEEP_INPUT and st.eig.nb2 == 0 and p > lib.gg_jacobi_max()
              and _env_int("GG_UPPER", 1) != 0)
     nparts_upper = lib.gg_mgl_upper_nparts(p) if kind == "mgl" else 0
     if upper:

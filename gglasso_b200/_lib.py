@@ -34,6 +34,7 @@ SIGNATURES = {
     "gg_prox_fsgl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp, _vp]),
     "gg_mgl_ntile": (_i, [_i]),
     "gg_mgl_upper_nparts": (_i, [_i]),
+    "gg_jacobi_max": (_i, []),
     "gg_prox_mgl_upper": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp]),
     "gg_build_w_upper": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "gg_mirror_upper": (_i, [_vp, _vp, _i, _i, _vp]),

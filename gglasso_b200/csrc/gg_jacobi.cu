@@ -400,6 +400,21 @@ bj_finalize_kernel(double* __restrict__ G, double* __restrict__ D, int p, BjStat
 // ==========================================================================================
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// matrices up to this size use the shared-memory Jacobi kernel (env GG_JACOBI_MAX, read once); it reads the FULL matrix,
+// the tridiagonal path above it only the upper triangle -- the host loop asks for this value (gg_jacobi_max)
+int gg_jacobi_small_max()
+{
+    static int small_max = -1;
+    if (small_max < 0) {
+        const char* ev = getenv("GG_JACOBI_MAX");
+        int v = ev ? atoi(ev) : GG_JACOBI_DEFAULT_MAX;
+        if (v > GG_SMALL_MAX) v = GG_SMALL_MAX;
+        if (v < 32) v = 32;          // the D&C leaves need n > 32
+        small_max = v;
+    }
+    return small_max;
+}
+
 size_t gg_tridiag_ws_bytes(int M, int n);
 int gg_eigh_tridiag_impl(double* A, double* D, int M, int n, const double* ctrl, int mpp, void* wsp, size_t ws_bytes,
                          cudaStream_t s, int which);
@@ -467,13 +482,7 @@ int gg_eigh_impl(double* A, double* D, int M, int p, const double* ctrl, int mpp
     if (tol <= 0.0) tol = fmax(1.0e-14, 8.0 * 2.220446049250313e-16 * sqrt((double)p));
     if (max_sweeps <= 0) max_sweeps = 30;
 
-    static int small_max = -1;          // matrices up to this size use the shared-memory Jacobi kernel
-    if (small_max < 0) {
-        const char* ev = getenv("GG_JACOBI_MAX");
-        small_max = ev ? atoi(ev) : GG_JACOBI_DEFAULT_MAX;
-        if (small_max > GG_SMALL_MAX) small_max = GG_SMALL_MAX;
-        if (small_max < 32) small_max = 32;          // the D&C leaves need n > 32
-    }
+    const int small_max = gg_jacobi_small_max();
     if (p <= small_max || (block_nb2 == 1 && p <= GG_SMALL_MAX)) {       // block_nb2 == 1 forces this path
         const int ld = p | 1;
         const size_t smem = sizeof(double) * (size_t)p * ld;

@@ -117,6 +117,7 @@ int gg_prox_mgl(const double* Omega, const double* Omega_prev, const double* L, 
  * lower triangles of up to two (M,p,p) stacks afterwards -- the mirroring of prox_p (ggl_helper.py:198-205) done once
  * instead of every iteration.  partials: gg_mgl_upper_nparts(p) * GG_NPART doubles.
  * gg_build_w_upper: W = Theta - X - (n_k/rho) S for i <= j (admm_solver.py:180), one problem of K instances. */
+int gg_jacobi_max(void);   /* largest p solved by the shared-memory Jacobi kernel (which reads the full matrix) */
 int gg_mgl_upper_nparts(int p);
 int gg_prox_mgl_upper(const double* Omega, const double* Omega_prev, double* X, double* Theta, const double* ctrl,
                       double lambda1, double lambda2, int reg, int K, int p, double* partials, void* stream);
