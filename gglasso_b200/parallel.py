@@ -199,6 +199,7 @@ def run_admm_mgl_dist(S_local, lambda1, lambda2, reg, Omega_0_local, K_total=Non
             dist.all_reduce(t, group=group)
         K_total = int(t.item())
     sh = KShard(K_total, p, group)
+    assert K_total >= sh.world, "K-sharded solve: every rank needs at least one instance (K_total >= world size)"
     assert sh.K_loc == K_loc, "each rank must hold partition(K_total, world)[rank] instances"
     nk = None if n_samples is None else np.asarray(n_samples, dtype=np.float64) * np.ones(K_loc)
     mu = None
